@@ -1,0 +1,70 @@
+"""ctypes binding of libfbdsp.so (include/fbdsp.h).  No fallback: if the library or a B200 is missing,
+the product raises instead of computing anything on the CPU."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .design import fb_psk_design
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("FBDSP_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libfbdsp.so"))
+
+FB_F32, FB_F64, FB_S16 = 0, 1, 2
+FB_SAMPLES_ON_DEVICE, FB_OUT_ON_DEVICE, FB_ASYNC = 1, 2, 4
+FB_ST_OK, FB_ST_EMPTY, FB_ST_TOO_SHORT, FB_ST_UNSUPPORTED = 0, 1, 2, 3
+
+# every symbol include/fbdsp.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "fb_abi_version", "fb_device_count", "fb_strerror", "fb_last_error", "fb_create", "fb_destroy", "fb_stream",
+    "fb_sync", "fb_kernel_launches", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
+]
+
+
+class FbdspError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FbdspError(f"{LIB_PATH} not found: build it with audio-modem-radio_b200/build.sh "
+                         f"(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, u64p, i64p, i32p, u8p = c.c_void_p, c.POINTER(c.c_uint64), c.POINTER(c.c_int64), c.POINTER(c.c_int32), c.c_void_p
+    lib.fb_abi_version.restype = c.c_int
+    lib.fb_device_count.restype = c.c_int
+    lib.fb_strerror.restype = c.c_char_p
+    lib.fb_strerror.argtypes = [c.c_int]
+    lib.fb_last_error.restype = c.c_char_p
+    lib.fb_last_error.argtypes = [vp]
+    lib.fb_create.restype = vp
+    lib.fb_create.argtypes = [c.c_int]
+    lib.fb_destroy.argtypes = [vp]
+    lib.fb_destroy.restype = None
+    lib.fb_stream.restype = vp
+    lib.fb_stream.argtypes = [vp]
+    lib.fb_sync.argtypes = [vp]
+    lib.fb_kernel_launches.restype = c.c_uint64
+    lib.fb_kernel_launches.argtypes = [vp]
+    lib.fb_psk_out_bound.restype = c.c_uint64
+    lib.fb_psk_out_bound.argtypes = [c.POINTER(fb_psk_design), c.c_uint64]
+    lib.fb_psk_demod_batch.restype = c.c_int
+    lib.fb_psk_demod_batch.argtypes = [vp, c.POINTER(fb_psk_design), vp, vp, c.c_int, vp, u64p, c.c_int, c.c_int,
+                                       u8p, u64p, vp, vp, vp]
+    lib.fb_psk_last_bits.restype = c.c_int
+    lib.fb_psk_last_bits.argtypes = [vp, c.c_int, vp, c.c_uint64, u64p]
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, rc: int, what: str):
+    if rc != 0:
+        detail = lib.fb_last_error(handle).decode() if handle else ""
+        raise FbdspError(f"{what}: {lib.fb_strerror(rc).decode()} {detail}".strip())

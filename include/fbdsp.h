@@ -1,0 +1,108 @@
+/* libfbdsp.so -- C ABI of the B200-native FileBeep batch demodulation engine.
+ *
+ * The reference (szumanski/Audio-Modem-Radio) has no FFI: its receive hot path is a set of
+ * Python module-level functions imported by name (decoder.py:12-14).  This header is the
+ * boundary a binding for that path talks to; each entry point cites the reference interface
+ * it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes, no torch / C++ types; caller owns every buffer;
+ * return 0 on success or a negative FB_E* code (fb_strerror); per-recording results carry
+ * their own FB_ST_* status so one bad recording never fails a batch.  One handle owns one
+ * CUDA stream and its device workspace; calls on one handle must not overlap, different
+ * handles are independent.  There is NO CPU fallback: every entry point that does work
+ * fails with FB_ECUDA when no sm_100 device is usable.
+ */
+#ifndef FBDSP_H
+#define FBDSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+/* sample storage of the input recordings */
+enum { FB_F32 = 0, FB_F64 = 1, FB_S16 = 2 };   /* S16: PCM16, value/32768 as soundfile does (decoder.py:381) */
+
+/* flags for *_batch calls */
+enum {
+  FB_SAMPLES_ON_DEVICE = 1,   /* `samples` is a device pointer (else host; pinned host copies fastest) */
+  FB_OUT_ON_DEVICE     = 2,   /* out / out_len / sync_idx / status are device pointers               */
+  FB_ASYNC             = 4    /* do not synchronise the handle's stream before returning              */
+};
+
+/* library return codes */
+enum { FB_OK = 0, FB_EINVAL = -1, FB_ECUDA = -2, FB_ENOMEM = -3, FB_EUNSUPPORTED = -4 };
+
+/* per-recording status */
+enum {
+  FB_ST_OK = 0,
+  FB_ST_EMPTY = 1,       /* fewer than 2 symbols: the reference returns b'' (modem.py:95-96, 211)          */
+  FB_ST_TOO_SHORT = 2,   /* N <= filtfilt padlen: the reference raises ValueError (scipy filtfilt)       */
+  FB_ST_UNSUPPORTED = 3  /* parameter set only servable by full-window evaluation and the record is too long */
+};
+
+typedef struct fb_handle fb_handle;
+
+/* Host-designed description of one DPSK parameter set (scheme, baud, carrier, fs).  Filter design
+ * (scipy.signal.butter, float64) stays in the host wrapper so coefficient parity with the reference
+ * is exact (modem.py:76,87,197,203); see audio-modem-radio_b200/fbdsp/design.py for every field. */
+#define FB_MAX_SLOW 4
+typedef struct fb_psk_design {
+  int32_t sps, n0, bits_per_sym;     /* int(fs/baud); first symbol instant; 1 = DBPSK slicer, 2 = DQPSK slicer */
+  int32_t nt, dl, dh;                /* polyphase taps per row; tap span in symbols: q in [-(dl*sps+sps-1), dh*sps] */
+  int32_t nslow, wcols;              /* slow conjugate pole pairs; warm-up length of their recursion (symbols) */
+  int32_t zone_left, zone_right;     /* samples near each end that belong to the edge kernel */
+  int32_t w_bp, w_lp;                /* decay lengths (samples) of the band-pass / low-pass recursions */
+  int32_t emulate_only, pad_bp, pad_lp, reserved;
+  double  cycles_per_sample;         /* carrier / fs */
+  double  bp_b[9], bp_a[9], bp_zi[8];/* butter(4, band) and lfilter_zi: what filtfilt runs (modem.py:76-77,197-198) */
+  double  lp_b[5], lp_a[5], lp_zi[4];/* butter(4, baud/nyq)                               (modem.py:87-88,203-204) */
+  float   rho[2];                    /* exp(-j 2 pi carrier sps / fs): the LO's rotation between two symbols */
+  double  slow_p[2 * FB_MAX_SLOW];
+  float   slow_lam[2 * FB_MAX_SLOW];
+  float   slow_rp[2 * FB_MAX_SLOW], slow_rpc[2 * FB_MAX_SLOW];
+  float   slow_rm[2 * FB_MAX_SLOW], slow_rmc[2 * FB_MAX_SLOW];
+} fb_psk_design;
+
+int         fb_abi_version(void);
+int         fb_device_count(void);                 /* number of usable CUDA devices (0 if none)            */
+const char* fb_strerror(int code);
+const char* fb_last_error(fb_handle* h);           /* text of the last CUDA failure on this handle         */
+
+fb_handle*  fb_create(int device);                 /* NULL when the device cannot be opened                */
+void        fb_destroy(fb_handle* h);
+void*       fb_stream(fb_handle* h);               /* the handle's cudaStream_t, for event timing / interop */
+int         fb_sync(fb_handle* h);
+uint64_t    fb_kernel_launches(fb_handle* h);      /* kernels launched by this handle so far               */
+
+/* Upper bound of the raw byte count one recording of n_samples can produce (size your `out` slots). */
+uint64_t    fb_psk_out_bound(const fb_psk_design* d, uint64_t n_samples);
+
+/* Batch DPSK demodulation: replaces bpsk_demodulate (modem.py:68-135), qpsk_demodulate
+ * (modem.py:189-266) and their aliases psk8_demodulate / ofdm_demodulate_simple / psk31_demodulate
+ * (modem.py:348,375,397) for n_rec independent recordings that share one parameter set.
+ *   taps      host, complex float [sps][nt]      (design.py PskDesign.taps)
+ *   slow_w    host, complex float [nslow][sps+1] (p^j)
+ *   samples   recordings back to back; recording r is samples[offsets[r] .. offsets[r+1])  (element units)
+ *   offsets, out_offsets   HOST arrays of n_rec+1 entries; out slot r is out[out_offsets[r] .. out_offsets[r+1])
+ *   out_len[r]   bytes written for recording r (what the reference returns as `bytes`)
+ *   sync_idx[r]  bit index where "0100011001000010" was first found (modem.py:118,248), -1 if absent
+ *   status[r]    FB_ST_*
+ */
+int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* d, const float* taps, const float* slow_w,
+                       int n_rec, const void* samples, const uint64_t* offsets, int dtype, int flags,
+                       uint8_t* out, const uint64_t* out_offsets,
+                       uint64_t* out_len, int64_t* sync_idx, int32_t* status);
+
+/* Debug / test hook: decided bit stream of the last fb_psk_demod_batch call on this handle
+ * (MSB-first packed, recording r at byte offset bit_offsets[r], n_bits[r] valid bits).  Host buffers. */
+int fb_psk_last_bits(fb_handle* h, int rec, uint8_t* bits_out, uint64_t cap_bytes, uint64_t* n_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBDSP_H */

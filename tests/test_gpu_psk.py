@@ -1,0 +1,115 @@
+"""-m gpu: the CUDA DPSK path through the C ABI against the golden fixtures and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import modem_v2 as o2, signals as sig
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+PSK_FNS = ("qpsk_demodulate", "psk8_demodulate", "ofdm_demodulate_simple", "bpsk_demodulate", "psk31_demodulate")
+
+
+def _cases():
+    cs = json.load(open(os.path.join(GOLD, "demod_cases.json")))["cases"]
+    return [c for c in cs if c["fn"] in PSK_FNS]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_golden_bytes(case, golden, engine):
+    """Bit-exact raw bytes (and the same exception type + text) as the reference on the stored inputs."""
+    from fbdsp import modem
+    _, arrs = golden
+    x = arrs[case["name"] + ".x"]
+    fn = getattr(modem, case["fn"])
+    if case["exc"]:
+        with pytest.raises(Exception) as ei:
+            fn(x, *case["args"])
+        assert type(ei.value).__name__ == case["exc"][0]
+        assert str(ei.value) == case["exc"][1]
+        return
+    raw = fn(x, *case["args"])
+    want = arrs[case["name"] + ".raw"].tobytes()
+    assert len(raw) == len(want)
+    assert raw == want
+
+
+def _bits_report(got, st, bps):
+    want = st["bits"]
+    assert len(got) == len(want)
+    bad = np.nonzero(got != want)[0]
+    margin = (o2.qpsk_margin if bps == 2 else o2.bpsk_margin)(st["diff"])
+    return bad, margin
+
+
+@pytest.mark.parametrize("baud,carrier,snr,seed", [(9600, 9600.0, 20, 101), (9600, 3000.0, 20, 102), (9600, 9600.0, 5, 103),
+                                                    (4800, 9600.0, 10, 104), (1200, 3000.0, 20, 105), (3000, 3000.0, 0, 106)])
+def test_qpsk_decisions_vs_oracle(baud, carrier, snr, seed, engine):
+    """Symbol decisions: >= 99.99 % equal, mismatches only where the oracle's margin < 1e-5 (north_star)."""
+    import fbdsp
+    nbytes = 20000 if baud >= 4800 else 2500
+    _, _, x = sig.kat_signal(sig.qpsk_modulate, seed, nbytes, snr, baud=baud, carrier=carrier)
+    d = fbdsp.psk_design(float(baud), float(carrier), 96000.0, 1.5, False)
+    res = engine.psk_demod_batch([x], d)[0]
+    st = o2.qpsk_stages(x, baud, carrier)
+    bad, margin = _bits_report(engine.last_bits(0), st, 2)
+    assert len(bad) <= 1e-4 * len(st["bits"])
+    assert all(margin[b // 2] < 1e-5 for b in bad), (bad[:10], margin[bad[:10] // 2])
+    if len(bad) == 0:
+        assert res.raw == st["raw"] and res.sync_idx == st["sync"]
+
+
+def test_bpsk_decisions_vs_oracle(engine):
+    import fbdsp
+    _, _, x = sig.kat_signal(sig.bpsk_modulate, 107, 6000, 10, baud=9600, carrier=3000.0)
+    d = fbdsp.psk_design(9600.0, 3000.0, 96000.0, 1.0, True)
+    res = engine.psk_demod_batch([x], d)[0]
+    st = o2.bpsk_stages(x, 9600, 3000.0)
+    bad, margin = _bits_report(engine.last_bits(0), st, 1)
+    assert all(margin[b] < 1e-5 for b in bad)
+    if len(bad) == 0:
+        assert res.raw == st["raw"]
+
+
+def test_ragged_batch_and_dtypes(engine):
+    """One launch over recordings of very different lengths (incl. too-short and empty ones) == one by one."""
+    import fbdsp
+    from fbdsp import _lib
+    rng = np.random.default_rng(7)
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    recs = []
+    for i, n in enumerate([50000, 10, 28, 3000, 123457, 40, 2700, 6000, 99999]):
+        if n > 5000:
+            _, _, x = sig.kat_signal(sig.qpsk_modulate, 200 + i, n // 45, 15, baud=9600, carrier=9600.0)
+            x = x[:n]
+        else:
+            x = (rng.standard_normal(n) * 0.2).astype(np.float32)
+        recs.append(x)
+    res = engine.psk_demod_batch(recs, d)
+    for x, r in zip(recs, res):
+        if len(x) <= 27:
+            assert r.status == _lib.FB_ST_TOO_SHORT and r.raw == b""
+            continue
+        want = o2.qpsk_stages(x, 9600, 9600.0)
+        assert r.raw == want["raw"], len(x)
+        assert r.sync_idx == want["sync"]
+    # float64 and PCM16 storage of the same (int16-exact) samples give the same bytes as the oracle on them
+    q = np.clip(np.round(recs[0] * 32767), -32768, 32767).astype(np.int16)
+    xf = q.astype(np.float32) / np.float32(32768.0)
+    want = o2.qpsk_demodulate(xf, 9600, 9600.0)
+    for arr in (xf, xf.astype(np.float64), q):
+        assert engine.psk_demod_batch([arr], d)[0].raw == want
+
+
+def test_shard_invariance_of_batching(engine):
+    """Any grouping / order of the same recordings gives identical per-recording bytes."""
+    import fbdsp
+    d = fbdsp.psk_design(9600.0, 3000.0, 96000.0, 1.5, False)
+    recs = [sig.kat_signal(sig.qpsk_modulate, 300 + i, 500 + 300 * i, 20, baud=9600, carrier=3000.0)[2] for i in range(6)]
+    whole = [r.raw for r in engine.psk_demod_batch(recs, d)]
+    rev = [r.raw for r in engine.psk_demod_batch(recs[::-1], d)][::-1]
+    single = [engine.psk_demod_batch([x], d)[0].raw for x in recs]
+    assert whole == rev == single
