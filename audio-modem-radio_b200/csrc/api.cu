@@ -66,7 +66,8 @@ extern "C" fb_handle* fb_create(int device) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess) {
     delete h;
     return nullptr;
   }
@@ -84,6 +85,8 @@ extern "C" void fb_destroy(fb_handle* h) {
     if (b->p) cudaFree(b->p);
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_join);
+  cudaEventDestroy(h->ev_k0);
+  cudaEventDestroy(h->ev_k1);
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->stream2);
   delete h;
@@ -100,3 +103,18 @@ extern "C" int fb_sync(fb_handle* h) {
 }
 
 extern "C" uint64_t fb_kernel_launches(fb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int fb_set_profiling(fb_handle* h, int on) {
+  if (!h) return FB_EINVAL;
+  h->profiling = on != 0;
+  h->k_recorded = false;
+  return FB_OK;
+}
+
+extern "C" float fb_kernel_ms(fb_handle* h) {
+  if (!h || !h->k_recorded) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(h->ev_k1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1) != cudaSuccess) return -1.f;
+  return ms;
+}

@@ -40,7 +40,8 @@ struct EdgeJob {
 struct fb_handle {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  bool profiling = false, k_recorded = false;
   uint64_t launches = 0;
   std::string err;
   // device workspace (grown on demand, never shrunk)

@@ -17,7 +17,7 @@ FB_ST_OK, FB_ST_EMPTY, FB_ST_TOO_SHORT, FB_ST_UNSUPPORTED = 0, 1, 2, 3
 # every symbol include/fbdsp.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "fb_abi_version", "fb_device_count", "fb_strerror", "fb_last_error", "fb_create", "fb_destroy", "fb_stream",
-    "fb_sync", "fb_kernel_launches", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
+    "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
 ]
 
 
@@ -53,6 +53,9 @@ def load() -> ctypes.CDLL:
     lib.fb_sync.argtypes = [vp]
     lib.fb_kernel_launches.restype = c.c_uint64
     lib.fb_kernel_launches.argtypes = [vp]
+    lib.fb_set_profiling.argtypes = [vp, c.c_int]
+    lib.fb_kernel_ms.restype = c.c_float
+    lib.fb_kernel_ms.argtypes = [vp]
     lib.fb_psk_out_bound.restype = c.c_uint64
     lib.fb_psk_out_bound.argtypes = [c.POINTER(fb_psk_design), c.c_uint64]
     lib.fb_psk_demod_batch.restype = c.c_int

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- FileBeep receive hot path on B200: DQPSK 9600 sym/s batch demodulation of 256 synthetic
+3-minute 96 kHz parts per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One process per GPU (torchrun for N > 1, weak scaling: every rank demodulates its own 256 recordings, no
+data-path collective).  A step = one pass of the hot path over the whole batch:
+psk_edge_kernel + psk_main_kernel + sync search + byte packing (+ frame parse/CRC on the host, untimed, for the
+payload figure -- see `config.frame_parse`).  `value` is timed with CUDA events on the engine's own stream with
+the batch resident in HBM; `e2e` goes through the host-buffer C-ABI call (pinned host samples -> H2D -> kernels
+-> D2H of the raw bytes) inside the timed region.  Inputs (17.7 GB per GPU) are far larger than L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "audio-modem-radio_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FS = 96000
+BAUD, CARRIER = 9600, 9600.0          # round-tripping DQPSK pair; raw-byte parity also holds at 3000
+METRIC = "demod Msamples/s (DQPSK 9600 sym/s, 3-min 96 kHz parts)"
+
+
+# ----------------------------------------------------------------------------------------- synthetic batch
+def make_recording_bits(k: int, n_samples: int, sps: int):
+    """Seeded payload -> FBPC frame -> DQPSK phase increments (host; needs CRC32 of the payload)."""
+    from oracle.frames import frame_data
+    rng = np.random.default_rng(1000 + k)
+    n_sym_max = n_samples // sps
+    payload_len = max(16, (n_sym_max - 40) // 4 - 64)          # fill the part: 4 symbols per byte + header + preamble
+    payload = rng.integers(0, 256, payload_len, dtype=np.uint8).tobytes()
+    framed = frame_data(f"part{k}.bin", payload, k, 256, payload_len * 256, 0)
+    bits = np.unpackbits(np.frombuffer(framed, dtype=np.uint8))
+    pre = np.array([0, 0] * 30 + [1, 1] * 10, dtype=np.uint8)    # modem.py:148
+    bits = np.concatenate([pre, bits])
+    code = bits[0::2].astype(np.int64) * 2 + bits[1::2]
+    table = np.array([0.0, np.pi / 2, -np.pi / 2, np.pi])         # modem.py:160-165
+    return payload_len, table[code]
+
+
+def synth_batch_device(torch, dev, n_rec: int, n_samples: int, snr_db: float, rank: int):
+    """DQPSK waveforms per modem.py:138-186 synthesised on the GPU with torch (set-up only, not the product),
+    zero-padded to n_samples, AWGN at snr_db over the whole record."""
+    sps = FS // BAUD
+    batch = torch.empty(n_rec * n_samples, dtype=torch.float32, device=dev)
+    t_sym = torch.arange(sps, device=dev, dtype=torch.float64) / FS
+    base = 2 * np.pi * CARRIER * t_sym
+    env = torch.ones(sps, dtype=torch.float64, device=dev)
+    ramp = int(sps * 0.1)
+    if ramp:
+        env[:ramp] = torch.linspace(0, 1, ramp, dtype=torch.float64, device=dev)
+        env[-ramp:] = torch.linspace(1, 0, ramp, dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
+    payload_bytes = 0
+    for k in range(n_rec):
+        plen, dphi = make_recording_bits(rank * n_rec + k, n_samples, sps)
+        payload_bytes += plen
+        ph = torch.cumsum(torch.from_numpy(dphi).to(dev), 0)
+        w = (torch.sin(base[None, :] + ph[:, None]) * env[None, :]).reshape(-1)
+        x = torch.zeros(n_samples, dtype=torch.float64, device=dev)
+        m = min(n_samples, w.numel())
+        x[:m] = w[:m]
+        gen.manual_seed(77000 + rank * n_rec + k)
+        sigma = float(torch.sqrt(torch.mean(x * x) / 10 ** (snr_db / 10)))
+        x += torch.randn(n_samples, generator=gen, device=dev, dtype=torch.float64) * sigma
+        batch[k * n_samples:(k + 1) * n_samples] = x.to(torch.float32)
+    return batch, payload_bytes
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:      # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:      # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    seed, n = args
+    from oracle import modem_v2 as o2, signals as sig
+    _, _, x = sig.kat_signal(sig.qpsk_modulate, seed, n // 40 - 64, 20, baud=BAUD, carrier=CARRIER)
+    x = np.concatenate([x, np.zeros(max(0, n - len(x)), np.float32)])[:n]
+    t = time.perf_counter()
+    raw = o2.qpsk_demodulate(x, BAUD, CARRIER)
+    return time.perf_counter() - t, len(x), len(raw)
+
+
+def cpu_baseline(seconds_per_rec: int = 30, reps: int = 1):
+    """Oracle port of modem.qpsk_demodulate on the host cores: one recording per worker process (the reference
+    code is single-threaded), bounded sample, throughput = samples / wall time of the parallel section."""
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    n = seconds_per_rec * FS
+    jobs = [(5000 + i, n) for i in range(cores * reps)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1, 2 * FS)] * cores)                 # import + warm up each worker
+        t = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t
+    samples = sum(r[1] for r in res)
+    single = float(np.mean([r[1] / r[0] for r in res])) / 1e6
+    return {"value": samples / wall / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "single_core_msamples_s": single,
+            "sample": f"{len(jobs)} x {seconds_per_rec}-s DQPSK recordings, oracle/modem_v2.qpsk_demodulate "
+                      f"(vectorised port of modem.py:189-266; faster than the reference's per-symbol Python loop), "
+                      f"one process per core"}
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fbdsp")
+    ap.add_argument("--recordings", type=int, default=256)
+    ap.add_argument("--seconds", type=int, default=180)
+    ap.add_argument("--snr", type=float, default=20.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"qpsk{BAUD}_c{int(CARRIER)}_{args.recordings}x{args.seconds}s_f32"
+    config = {"workload": workload, "scheme": "DQPSK (modem.qpsk_demodulate)", "baud": BAUD, "carrier_hz": CARRIER,
+              "fs_hz": FS, "recordings_per_gpu": args.recordings, "seconds_per_recording": args.seconds,
+              "snr_db": args.snr, "sample_dtype": "float32", "l2": "inputs (GBs) larger than L2, no flush needed",
+              "sharding": "independent recordings per rank, no collective in the data path"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        for _ in range(max(0, args.warmup)):
+            cpu_baseline(5)
+        vals = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cb = cpu_baseline(20)
+            vals.append(cb["value"])
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        v = float(np.mean(vals))
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import fbdsp
+    from fbdsp import _lib
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = fbdsp.Engine(local)
+    d = fbdsp.psk_design(float(BAUD), float(CARRIER), float(FS), 1.5, False)
+    n_rec, n_samp = args.recordings, args.seconds * FS
+    batch, payload_bytes_in = synth_batch_device(torch, dev, n_rec, n_samp, args.snr, rank)
+    torch.cuda.synchronize()
+    offsets = (np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(n_samp))
+    out_offsets = eng.out_bounds(d, [n_samp] * n_rec)
+    out_dev = torch.empty(int(out_offsets[-1]) + 16, dtype=torch.uint8, device=dev)
+    out_len = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+    sync_idx = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+    status = torch.zeros(n_rec, dtype=torch.int32, device=dev)
+    flags = _lib.FB_SAMPLES_ON_DEVICE | _lib.FB_OUT_ON_DEVICE | _lib.FB_ASYNC
+    es = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def step():
+        eng.psk_demod_raw(d, batch.data_ptr(), offsets, _lib.FB_F32, flags, out_dev.data_ptr(), out_offsets,
+                          out_len.data_ptr(), sync_idx.data_ptr(), status.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        eng.sync()
+        torch.cuda.synchronize()
+
+    eng.lib.fb_set_profiling(eng.handle, 1)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.kernel_launches
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kernel_ms = []
+    barrier()
+    ev[0].record(es)
+    for _ in range(args.steps):
+        step()
+    ev[1].record(es)
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[1])
+    launches = eng.kernel_launches - launches0
+    # dominant-kernel duration, CUDA events on its own stream: re-run K profiled steps one at a time
+    kernel_ms = []
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(float(eng.lib.fb_kernel_ms(eng.handle)))
+    barrier()
+    clk = clocks.stop()
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    samples_per_step = n_rec * n_samp * world
+    value = samples_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # results of the last step: raw bytes, frames (host parse + CRC32, untimed), parity spot check vs the oracle
+    ol = out_len.cpu().numpy()
+    raw_bytes = int(ol.sum())
+    out_host = out_dev.cpu().numpy()
+    from oracle.frames import parse_fbp_stream
+    payload_ok = 0
+    for r in range(n_rec):
+        o = int(out_offsets[r])
+        for fr in parse_fbp_stream(out_host[o:o + int(ol[r])].tobytes()):
+            payload_ok += len(fr["data"])
+    if dist is not None:
+        t = torch.tensor([raw_bytes, payload_ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        raw_all, payload_all = float(t[0]), float(t[1])
+    else:
+        raw_all, payload_all = float(raw_bytes), float(payload_ok)
+
+    # ---- e2e: host-buffer C-ABI call, pinned samples, H2D + kernels + D2H of the raw bytes inside the timed region
+    e2e = None
+    try:
+        if args.no_e2e:
+            raise RuntimeError('skipped (--no-e2e)')
+        host = torch.empty(batch.numel(), dtype=torch.float32, pin_memory=True)
+        host.copy_(batch)
+        out_h = torch.empty(int(out_offsets[-1]) + 16, dtype=torch.uint8, pin_memory=True)
+        ol_h = torch.zeros(n_rec, dtype=torch.int64, pin_memory=True)
+        sy_h = torch.zeros(n_rec, dtype=torch.int64, pin_memory=True)
+        st_h = torch.zeros(n_rec, dtype=torch.int32, pin_memory=True)
+
+        def step_e2e():
+            eng.psk_demod_raw(d, host.data_ptr(), offsets, _lib.FB_F32, 0, out_h.data_ptr(), out_offsets,
+                              ol_h.data_ptr(), sy_h.data_ptr(), st_h.data_ptr())
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert int(ol_h.sum()) == raw_bytes, "host-buffer path disagrees with the device-resident path"
+        e2e = {"value": samples_per_step / e2e_s / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": int(batch.numel() * 4), "d2h_bytes_per_step": int(out_offsets[-1]) + n_rec * 20,
+               "steps": args.e2e_steps, "api": "fb_psk_demod_batch(host pointers) via fbdsp.Engine.psk_demod_raw"}
+    except RuntimeError as e:       # pinned allocation can fail on a small host
+        e2e = {"value": None, "unit": "Msamples/s", "error": str(e)[:200]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:      # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = float(np.mean([k for k in kernel_ms if k and k > 0])) if kernel_ms else float("nan")
+    alg_bytes = n_rec * n_samp * 4 + raw_bytes
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "psk_main_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "note": "fp32-FMA co-limited: ~46 FMA per sample (DESIGN.md); traffic from profiles/ ncu capture"}
+    cb = None if args.no_cpu else cpu_baseline(30)
+    line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(config, frame_parse="host (oracle parser + zlib CRC32), untimed; GPU parser pending"),
+            "raw_MB_per_s": raw_all / (ms_per_step * 1e-3) / 1e6, "payload_MB_per_s": payload_all / (ms_per_step * 1e-3) / 1e6,
+            "payload_bytes_valid": payload_all, "payload_bytes_sent_rank0": payload_bytes_in,
+            "gsamples_per_s_per_gpu": value / 1e3 / world, "gpu_launches": int(launches), "clocks": clk,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

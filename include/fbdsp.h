@@ -79,6 +79,12 @@ void*       fb_stream(fb_handle* h);               /* the handle's cudaStream_t,
 int         fb_sync(fb_handle* h);
 uint64_t    fb_kernel_launches(fb_handle* h);      /* kernels launched by this handle so far               */
 
+/* Per-kernel device timing for roofline accounting (bench.py): when enabled, CUDA events are recorded on the
+ * launching stream right before and after the dominant kernel of each *_batch call; fb_kernel_ms returns the
+ * duration of the most recent one (blocks until it has finished), or a negative value if none was recorded. */
+int         fb_set_profiling(fb_handle* h, int on);
+float       fb_kernel_ms(fb_handle* h);
+
 /* Upper bound of the raw byte count one recording of n_samples can produce (size your `out` slots). */
 uint64_t    fb_psk_out_bound(const fb_psk_design* d, uint64_t n_samples);
 
