@@ -18,7 +18,17 @@ FB_ST_OK, FB_ST_EMPTY, FB_ST_TOO_SHORT, FB_ST_UNSUPPORTED = 0, 1, 2, 3
 SYMBOLS = [
     "fb_abi_version", "fb_device_count", "fb_strerror", "fb_last_error", "fb_create", "fb_destroy", "fb_stream",
     "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
+    "fb_rs_out_bound", "fb_viterbi_out_bound", "fb_rs_decode_batch", "fb_viterbi_decode_batch", "fb_crc32_batch",
+    "fb_parse_frames_batch",
 ]
+
+
+class fb_frame(ctypes.Structure):
+    """Mirror of `struct fb_frame` in include/fbdsp.h."""
+    _fields_ = [("offset", ctypes.c_uint64), ("name_off", ctypes.c_uint64), ("payload_off", ctypes.c_uint64),
+                ("name_len", ctypes.c_uint32), ("part", ctypes.c_uint32), ("total", ctypes.c_uint32),
+                ("file_size", ctypes.c_uint32), ("file_crc", ctypes.c_uint32), ("data_len", ctypes.c_uint32),
+                ("payload_crc", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class FbdspError(RuntimeError):
@@ -63,6 +73,18 @@ def load() -> ctypes.CDLL:
                                        u8p, u64p, vp, vp, vp]
     lib.fb_psk_last_bits.restype = c.c_int
     lib.fb_psk_last_bits.argtypes = [vp, c.c_int, vp, c.c_uint64, u64p]
+    lib.fb_rs_out_bound.restype = c.c_uint64
+    lib.fb_rs_out_bound.argtypes = [c.c_uint64]
+    lib.fb_viterbi_out_bound.restype = c.c_uint64
+    lib.fb_viterbi_out_bound.argtypes = [c.c_uint64]
+    lib.fb_rs_decode_batch.restype = c.c_int
+    lib.fb_rs_decode_batch.argtypes = [vp, c.c_int, vp, u64p, vp, u64p, vp, vp, c.c_int]
+    lib.fb_viterbi_decode_batch.restype = c.c_int
+    lib.fb_viterbi_decode_batch.argtypes = [vp, c.c_int, vp, u64p, vp, u64p, vp, c.c_int]
+    lib.fb_crc32_batch.restype = c.c_int
+    lib.fb_crc32_batch.argtypes = [vp, c.c_int, vp, u64p, vp, c.c_int]
+    lib.fb_parse_frames_batch.restype = c.c_int
+    lib.fb_parse_frames_batch.argtypes = [vp, c.c_int, vp, u64p, vp, c.c_int, vp, vp, vp, c.c_int]
     _lib = lib
     return lib
 

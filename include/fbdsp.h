@@ -108,6 +108,38 @@ int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* d, const float* taps, 
  * (MSB-first packed, recording r at byte offset bit_offsets[r], n_bits[r] valid bits).  Host buffers. */
 int fb_psk_last_bits(fb_handle* h, int rec, uint8_t* bits_out, uint64_t cap_bytes, uint64_t* n_bits);
 
+/* ---- fec.py decode (standalone ops: the reference never wires FEC into decode_from_buffer) ------------------
+ * Blocks are independent; block i is in[in_offsets[i] .. in_offsets[i+1]), its slot out[out_offsets[i] ..
+ * out_offsets[i+1]) (size it with fb_*_out_bound).  in_offsets / out_offsets are HOST arrays of n_blk+1 entries;
+ * FB_SAMPLES_ON_DEVICE says `in` is a device pointer, FB_OUT_ON_DEVICE says out / out_len / crc_ok are.          */
+uint64_t fb_rs_out_bound(uint64_t n);          /* ReedSolomonFEC.decode output length for n input bytes (fec.py:34-69) */
+uint64_t fb_viterbi_out_bound(uint64_t n);     /* ViterbiDecoder.decode output length (fec.py:126-155)                */
+/* Replaces ReedSolomonFEC.decode (fec.py:34-69).  crc_ok[i] = 1 when the trailing CRC32 matches the decoded block
+ * (the reference only prints a warning when it does not), 0 otherwise, -1 when the out slot is too small.          */
+int fb_rs_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
+                       const uint64_t* out_offsets, uint64_t* out_len, int32_t* crc_ok, int flags);
+/* Replaces ViterbiDecoder.decode (fec.py:126-155). */
+int fb_viterbi_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
+                            const uint64_t* out_offsets, uint64_t* out_len, int flags);
+/* zlib.crc32 / binascii.crc32 of n_blk byte ranges (decoder.py:100,194; fec.py:65). */
+int fb_crc32_batch(fb_handle* h, int n_blk, const uint8_t* data, const uint64_t* offsets, uint32_t* crc, int flags);
+
+/* ---- FBPC frame parser: replaces decoder.parse_fbp_stream_enhanced (decoder.py:142-208) -------------------------
+ * Frame layout (encoder.py:94-114): "FBPC" | u8 name_len | name | <6 x u32 LE: part, total, file_size, file_crc,
+ * data_len, crc32(data)> | data.  Offsets in fb_frame are relative to the recording's raw stream.                   */
+typedef struct fb_frame {
+  uint64_t offset, name_off, payload_off;
+  uint32_t name_len, part, total, file_size, file_crc, data_len, payload_crc, reserved;
+} fb_frame;
+/* raw stream of recording r: raw[raw_offsets[r] ..) with raw_len[r] valid bytes (raw_offsets HOST, n_rec+1 entries;
+ * raw_len lives where `raw` lives: device when FB_SAMPLES_ON_DEVICE -- e.g. fb_psk_demod_batch's out / out_len).
+ * frames: n_rec * max_frames records, CRC-valid frames of recording r in stream order at frames[r*max_frames ..];
+ * n_frames[r] = count (may exceed max_frames: only the first max_frames are stored; negative = more than 64 "FBPC"
+ * candidates, re-parse that recording on the host); payload_bytes[r] = sum of their data_len.                       */
+int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw, const uint64_t* raw_offsets,
+                          const uint64_t* raw_len, int max_frames, fb_frame* frames, int32_t* n_frames,
+                          uint64_t* payload_bytes, int flags);
+
 #ifdef __cplusplus
 }
 #endif

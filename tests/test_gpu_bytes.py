@@ -1,0 +1,84 @@
+"""-m gpu: FEC decode, CRC32 and the FBPC frame parser kernels against the reference's own vectors and the oracle."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import fec as ofec, frames as ofr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fec_golden_vectors(engine):
+    from fbdsp import fec
+    vec = json.load(open(os.path.join(GOLD, "fec.json")))
+    rs_in = [bytes.fromhex(v["inp"]) for v in vec if v["op"] == "rs"]
+    rs_out = [bytes.fromhex(v["out"]) for v in vec if v["op"] == "rs"]
+    got = fec.rs_decode_batch(rs_in, engine)
+    assert [g[0] for g in got] == rs_out
+    assert [g[1] for g in got] == [ofec.rs_decode_ex(b)[1] for b in rs_in]
+    vi_in = [bytes.fromhex(v["inp"]) for v in vec if v["op"] == "vit"]
+    vi_out = [bytes.fromhex(v["out"]) for v in vec if v["op"] == "vit"]
+    assert fec.viterbi_decode_batch(vi_in, engine) == vi_out
+
+
+def test_fec_classes_match_reference_api(engine):
+    from fbdsp import fec
+    assert fec.ReedSolomonFEC(nsym=32).decode(bytes.fromhex("68650d6c6c006fff86a61036")).hex() == "68656c6c6fff"
+    assert fec.ReedSolomonFEC().decode(b"abc") == b"abc"
+    assert fec.ViterbiDecoder(constraint_length=7).decode(bytes.fromhex("391615f24d92ee22ee2ca607")).hex() == "610d29f5f603"
+    assert fec.ViterbiDecoder().decode(b"") == b"" and fec.ViterbiDecoder().decode(b"\xa5").hex() == "0c"
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 518400, 777604, 3_000_001])
+def test_fec_large_blocks_vs_oracle(n, engine):
+    """Part-sized blocks (config 3: 518 400-byte parts, x1.5 + 4 when RS-encoded), ragged batch."""
+    from fbdsp import fec
+    rng = np.random.default_rng(n)
+    data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    enc = ofec.rs_encode(data)
+    bad = bytearray(enc)
+    if len(bad) > 10:
+        bad[7] ^= 0x55
+    blocks = [enc, bytes(bad), data]
+    got = fec.rs_decode_batch(blocks, engine)
+    for b, (dec, ok) in zip(blocks, got):
+        want, wok = ofec.rs_decode_ex(b)
+        assert dec == want and ok == wok
+    conv = ofec.conv_encode(data[: 200000])
+    assert fec.viterbi_decode_batch([conv, data], engine) == [ofec.viterbi_decode(conv), ofec.viterbi_decode(data)]
+    # round trip property at full size: decode(encode(x)) == x, CRC ok; odd lengths come back with the 0xFF pad
+    # byte appended and therefore (in the reference too) always fail the CRC check
+    dec, ok = got[0]
+    assert dec == data + (b"\xff" if n % 2 else b"") and ok == (n % 2 == 0)
+
+
+def test_crc32_matches_zlib(engine):
+    from fbdsp import fec
+    rng = np.random.default_rng(3)
+    blocks = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (0, 1, 2, 3, 4, 5, 15, 16, 17, 255, 4097, 431000, 1 << 20)]
+    assert fec.crc32_batch(blocks, engine) == [zlib.crc32(b) & 0xFFFFFFFF for b in blocks]
+
+
+def test_frame_parser_golden(engine):
+    from fbdsp import frames
+    vec = json.load(open(os.path.join(GOLD, "frames.json")))
+    names = list(vec)
+    got = frames.parse_batch([bytes.fromhex(vec[k]["stream"]) for k in names], engine)
+    for k, g in zip(names, got):
+        want = [dict(name=f["name"], data=bytes.fromhex(f["data"]), final_crc=f["final_crc"]) for f in vec[k]["frames"]]
+        assert g == want, k
+
+
+def test_frame_parser_big_stream_vs_oracle(engine):
+    from fbdsp import frames
+    rng = np.random.default_rng(9)
+    p = rng.integers(0, 256, 431000, dtype=np.uint8).tobytes()
+    s = rng.integers(0, 256, 777, dtype=np.uint8).tobytes() + ofr.frame_data("part7.bin", p, 7, 256, 1 << 30, 0xABCDEF01) + b"FBPC" * 3
+    corrupted = bytearray(s); corrupted[5000] ^= 1
+    got = frames.parse_batch([s, bytes(corrupted), b""], engine, full=True)
+    assert got[0] == ofr.parse_fbp_stream(s, full=True)
+    assert got[1] == [] and got[2] == []
