@@ -34,6 +34,8 @@ class DemodResult:
 def _as_samples(x) -> np.ndarray:
     """What the reference's numpy/scipy code would make of `samples`: any real array-like becomes float;
     float32 and float64 are passed through untouched (no copy), everything else is promoted to float64."""
+    if type(x).__name__ == "_Pcm16":       # decoder.decode_wav_file: PCM16 straight from the WAV (device scales by 1/32768)
+        return np.ascontiguousarray(x.pcm, dtype=np.int16)
     a = np.asarray(x)
     if a.ndim != 1:
         a = a.reshape(-1) if a.ndim == 0 else a
