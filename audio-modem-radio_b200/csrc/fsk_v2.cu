@@ -1,0 +1,284 @@
+// v2 FSK receive chain on sm_100a: replaces fsk_demodulate (modem.py:298-341) for valid tone sets.
+//
+// Per tone (modem.py:306-309):  f = filtfilt(butter(3, [f-b, f+b]), x);  env = |hilbert(f)|
+//   iir_fwd_kernel / iir_bwd_kernel   scipy.signal.filtfilt in float64: odd extension by padlen, lfilter_zi start-up,
+//                                     DF2T forward then backward.  Chunk-parallel: one thread per chunk of the
+//                                     extended record, exact state at the true ends, zero state + `w` warm-up samples
+//                                     (pole decay to 1e-12) at interior cuts.
+//   cuFFT D2Z -> analytic_fill -> cuFFT Z2Z inverse   scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and
+//                                     one length-N inverse FFT over the whole recording (circular); the library FFT is
+//                                     used for this one library-shaped op exactly as the reference uses pocketfft.
+// Decision (modem.py:315-323): bits[n] = env_mark[n] > env_space[n]; per bit a majority vote over the centre half
+// (window truncated at the record end; spb < 4 -> empty window -> no bits).  fsk_vote_kernel packs the decided bits
+// into the same big-endian word stream the DPSK kernels write; backend.cu does the magic search and byte packing.
+#include "common.cuh"
+
+#include <cufft.h>
+#include <algorithm>
+#include <map>
+
+#define FSK_ORD 6            // butter(3, band) -> 6th order, 7 coefficients
+#define FSK_CHUNK 2048
+
+struct FskTone {
+  double b[FSK_ORD + 1], a[FSK_ORD + 1], zi[FSK_ORD];
+  int32_t w, pad;
+};
+
+template <typename TIn>
+__device__ __forceinline__ double fsk_x_ext(const void* samples, uint64_t off, int64_t N, int64_t n) {
+  if (n < 0) return 2.0 * load_sample_d<TIn>(samples, off) - load_sample_d<TIn>(samples, off + (uint64_t)(-n));
+  if (n > N - 1)
+    return 2.0 * load_sample_d<TIn>(samples, off + (uint64_t)(N - 1)) - load_sample_d<TIn>(samples, off + (uint64_t)(2 * (N - 1) - n));
+  return load_sample_d<TIn>(samples, off + (uint64_t)n);
+}
+
+// forward pass over the extended record e in [0, Next), ext[e] = x_ext(e - pad); writes yfwd[e]
+template <typename TIn>
+__global__ void __launch_bounds__(64) iir_fwd_kernel(const void* samples, uint64_t off, int64_t N, FskTone t, double* yfwd) {
+  const int64_t Next = N + 2 * t.pad;
+  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * FSK_CHUNK;
+  if (c0 >= Next) return;
+  const int64_t c1 = min(Next, c0 + FSK_CHUNK);
+  const int64_t s = max((int64_t)0, c0 - t.w);
+  double z[FSK_ORD];
+  const double x0 = fsk_x_ext<TIn>(samples, off, N, s - t.pad);
+#pragma unroll
+  for (int i = 0; i < FSK_ORD; ++i) z[i] = (s == 0) ? t.zi[i] * x0 : 0.0;
+  constexpr int EB = 16;
+  for (int64_t e0 = s; e0 < c1; e0 += EB) {
+    double xb[EB];
+#pragma unroll
+    for (int u = 0; u < EB; ++u) xb[u] = (e0 + u < c1) ? fsk_x_ext<TIn>(samples, off, N, e0 + u - t.pad) : 0.0;
+#pragma unroll
+    for (int u = 0; u < EB; ++u) {
+      const double xv = xb[u];
+      const double y = t.b[0] * xv + z[0];
+#pragma unroll
+      for (int k = 0; k < FSK_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
+      z[FSK_ORD - 1] = t.b[FSK_ORD] * xv - t.a[FSK_ORD] * y;
+      if (e0 + u >= c0 && e0 + u < c1) yfwd[e0 + u] = y;
+    }
+  }
+}
+
+// backward pass over yfwd; writes f[n] for the un-extended record
+__global__ void __launch_bounds__(64) iir_bwd_kernel(const double* yfwd, int64_t N, FskTone t, double* f) {
+  const int64_t Next = N + 2 * t.pad;
+  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * FSK_CHUNK;
+  if (c0 >= Next) return;
+  const int64_t c1 = min(Next, c0 + FSK_CHUNK);
+  const int64_t s = min(Next - 1, c1 - 1 + t.w);           // first (highest) index processed
+  double z[FSK_ORD];
+  const double y0 = yfwd[s];
+#pragma unroll
+  for (int i = 0; i < FSK_ORD; ++i) z[i] = (s == Next - 1) ? t.zi[i] * y0 : 0.0;
+  constexpr int EB = 16;
+  for (int64_t e0 = s; e0 >= c0; e0 -= EB) {
+    double xb[EB];
+#pragma unroll
+    for (int u = 0; u < EB; ++u) xb[u] = (e0 - u >= c0) ? yfwd[e0 - u] : 0.0;
+#pragma unroll
+    for (int u = 0; u < EB; ++u) {
+      const int64_t e = e0 - u;
+      if (e >= c0) {
+        const double xv = xb[u];
+        const double y = t.b[0] * xv + z[0];
+#pragma unroll
+        for (int k = 0; k < FSK_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
+        z[FSK_ORD - 1] = t.b[FSK_ORD] * xv - t.a[FSK_ORD] * y;
+        const int64_t n = e - t.pad;
+        if (e < c1 && n >= 0 && n < N) f[n] = y;
+      }
+    }
+  }
+}
+
+// scipy.signal.hilbert's one-sided mask: h[0] = 1, h[1 .. ceil(N/2)-1] = 2, h[N/2] = 1 (N even), 0 above
+__global__ void __launch_bounds__(FB_THREADS) analytic_fill_kernel(const cufftDoubleComplex* X, cufftDoubleComplex* Z, int64_t N) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    cufftDoubleComplex v = make_cuDoubleComplex(0.0, 0.0);
+    if (k <= N / 2) {
+      const double h = (k == 0 || (2 * k == N)) ? 1.0 : 2.0;
+      if (k < (N + 1) / 2 || 2 * k == N) { v = X[k]; v.x *= h; v.y *= h; }
+    }
+    Z[k] = v;
+  }
+}
+
+// first tone: keep |a|^2; second tone: cmp[n] = env_mark > env_space  (common 1/N scale dropped on both sides)
+__global__ void __launch_bounds__(FB_THREADS) env_kernel(const cufftDoubleComplex* Z, int64_t N, double* env2, uint8_t* cmp, int second) {
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const double e = hypot(Z[n].x, Z[n].y);
+    if (!second) env2[n] = e;
+    else cmp[n] = env2[n] > e ? 1 : 0;
+  }
+}
+
+// majority vote per bit (modem.py:320-323), 32 bits per thread, big-endian words
+__global__ void __launch_bounds__(FB_THREADS) fsk_vote_kernel(const uint8_t* cmp, int64_t N, int spb, int64_t nbits, uint32_t* words) {
+  const int64_t nwords = (nbits + 31) / 32;
+  const int q = spb / 4;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t word = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int64_t i = w * 32 + k;
+      uint32_t bit = 0;
+      if (i < nbits) {
+        const int64_t c = spb / 2 + i * spb;
+        const int64_t lo = c - q, hi = min(c + q, N);
+        int ones = 0;
+        for (int64_t n = lo; n < hi; ++n) ones += cmp[n];
+        bit = (2 * ones > (int)(hi - lo)) ? 1u : 0u;       // np.mean(chunk) > 0.5
+      }
+      word = (word << 1) | bit;
+    }
+    words[w] = __byte_perm(word, 0, 0x0123);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct FskPlans {
+  std::map<int64_t, std::pair<cufftHandle, cufftHandle>> plans;   // N -> (D2Z, Z2Z)
+};
+static std::map<fb_handle*, FskPlans> g_fsk_plans;
+
+void fb_fsk_release(fb_handle* h) {
+  auto it = g_fsk_plans.find(h);
+  if (it == g_fsk_plans.end()) return;
+  for (auto& p : it->second.plans) { cufftDestroy(p.second.first); cufftDestroy(p.second.second); }
+  g_fsk_plans.erase(it);
+}
+
+template <typename TIn>
+static int fsk_one(fb_handle* h, const fb_fsk_design& d, const void* d_samples, uint64_t off, int64_t N, int64_t nbits,
+                   uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2z, double* yfwd, double* f,
+                   cufftDoubleComplex* X, cufftDoubleComplex* Z, double* env, uint8_t* cmp) {
+  for (int tone = 0; tone < 2; ++tone) {
+    FskTone t;
+    for (int i = 0; i <= FSK_ORD; ++i) { t.b[i] = d.b[tone][i]; t.a[i] = d.a[tone][i]; }
+    for (int i = 0; i < FSK_ORD; ++i) t.zi[i] = d.zi[tone][i];
+    t.w = d.w[tone]; t.pad = d.pad;
+    const int64_t Next = N + 2 * d.pad;
+    const int nthreads = (int)((Next + FSK_CHUNK - 1) / FSK_CHUNK);
+    const int nblocks = (nthreads + 63) / 64;
+    iir_fwd_kernel<TIn><<<nblocks, 64, 0, h->stream>>>(d_samples, off, N, t, yfwd);
+    iir_bwd_kernel<<<nblocks, 64, 0, h->stream>>>(yfwd, N, t, f);
+    if (cufftExecD2Z(p_d2z, f, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
+    const int g = (int)std::min<int64_t>(148 * 8, (N + FB_THREADS - 1) / FB_THREADS);
+    analytic_fill_kernel<<<g, FB_THREADS, 0, h->stream>>>(X, Z, N);
+    if (cufftExecZ2Z(p_z2z, Z, Z, CUFFT_INVERSE) != CUFFT_SUCCESS) { h->err = "cufftExecZ2Z failed"; return FB_ECUDA; }
+    env_kernel<<<g, FB_THREADS, 0, h->stream>>>(Z, N, env, cmp, tone);
+    h->launches += 4;
+  }
+  if (nbits > 0) {
+    const int g = (int)std::min<int64_t>(148 * 8, ((nbits + 31) / 32 + FB_THREADS - 1) / FB_THREADS);
+    fsk_vote_kernel<<<g, FB_THREADS, 0, h->stream>>>(cmp, N, d.spb, nbits, d_words);
+    h->launches++;
+  }
+  FB_CUDA(h, cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" uint64_t fb_fsk_out_bound(const fb_fsk_design* d, uint64_t n_samples) {
+  if (!d || d->spb < 1 || d->spb / 4 == 0) return 0;
+  const int64_t N = (int64_t)n_samples, c0 = d->spb / 2;
+  const int64_t nbits = N > c0 ? (N - c0 + d->spb - 1) / d->spb : 0;
+  return (uint64_t)(nbits / 8);
+}
+
+extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_rec, const void* samples, const uint64_t* offsets,
+                                  int dtype, int flags, uint8_t* out, const uint64_t* out_offsets, uint64_t* out_len,
+                                  int64_t* sync_idx, int32_t* status) {
+  if (!h || !dp || n_rec < 0 || !offsets || !out_offsets) return FB_EINVAL;
+  if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
+  const fb_fsk_design& d = *dp;
+  if (d.spb < 1 || d.pad < 1) return FB_EINVAL;
+  FB_CUDA(h, cudaSetDevice(h->device));
+  if (n_rec == 0) return FB_OK;
+  const size_t esz = dtype == FB_F32 ? 4 : dtype == FB_F64 ? 8 : 2;
+  std::vector<RecPlan> plans(n_rec);
+  uint64_t words = 0;
+  int64_t maxN = 0;
+  for (int r = 0; r < n_rec; ++r) {
+    RecPlan& p = plans[r];
+    p.off = offsets[r]; p.n = offsets[r + 1] - offsets[r];
+    p.out_off = out_offsets[r]; p.out_cap = out_offsets[r + 1] - out_offsets[r];
+    p.word_off = words; p.dl32 = p.dr32 = 0; p.nsym = 0; p.ndsym = 0; p.status = FB_ST_OK; p.pad = 0;
+    const int64_t N = (int64_t)p.n;
+    if (N <= d.pad) { p.status = FB_ST_TOO_SHORT; continue; }
+    if (N > ((int64_t)1 << 31) - 64) { p.status = FB_ST_UNSUPPORTED; continue; }
+    const int64_t c0 = d.spb / 2;
+    int64_t nbits = (d.spb / 4 > 0 && N > c0) ? (N - c0 + d.spb - 1) / d.spb : 0;   // len(range(spb//2, N, spb)); q == 0 -> none
+    p.nsym = p.ndsym = (int32_t)nbits;                                              // backend reads ndsym * bps bits
+    words += ((uint64_t)nbits + 31) / 32 + 2;
+    maxN = std::max(maxN, N);
+  }
+  const uint64_t total_samples = offsets[n_rec], total_out = out_offsets[n_rec];
+  const void* d_samples = samples;
+  int rc;
+  if (!(flags & FB_SAMPLES_ON_DEVICE)) {
+    if ((rc = fb_ensure(h, h->in, (size_t)total_samples * esz + 16))) return rc;
+    FB_CUDA(h, cudaMemcpyAsync(h->in.p, samples, (size_t)total_samples * esz, cudaMemcpyHostToDevice, h->stream));
+    d_samples = h->in.p;
+  }
+  uint8_t* d_out = out; uint64_t* d_out_len = out_len; int64_t* d_sync = sync_idx; int32_t* d_status = status;
+  if (!(flags & FB_OUT_ON_DEVICE)) {
+    if ((rc = fb_ensure(h, h->out, (size_t)total_out + 16))) return rc;
+    if ((rc = fb_ensure(h, h->out_len, (size_t)n_rec * 8))) return rc;
+    if ((rc = fb_ensure(h, h->sync_idx, (size_t)n_rec * 8))) return rc;
+    if ((rc = fb_ensure(h, h->status, (size_t)n_rec * 4))) return rc;
+    d_out = (uint8_t*)h->out.p; d_out_len = (uint64_t*)h->out_len.p; d_sync = (int64_t*)h->sync_idx.p; d_status = (int32_t*)h->status.p;
+  }
+  if ((rc = fb_ensure(h, h->bits, (size_t)(words + 4) * 4))) return rc;
+  if ((rc = fb_ensure(h, h->plans, (size_t)n_rec * sizeof(RecPlan)))) return rc;
+  FB_CUDA(h, cudaMemcpyAsync(h->plans.p, plans.data(), (size_t)n_rec * sizeof(RecPlan), cudaMemcpyHostToDevice, h->stream));
+  // scratch for the longest recording: yfwd | f | X | Z | env | cmp
+  const size_t nE = (size_t)maxN + 2 * d.pad + 16, nN = (size_t)maxN + 16;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };            // cuFFT wants 16-byte aligned complex buffers
+  const size_t o_f = al(nE * 8), o_X = al(o_f + nN * 8), o_Z = al(o_X + (nN / 2 + 2) * 16), o_env = al(o_Z + nN * 16), o_cmp = al(o_env + nN * 8);
+  if (maxN > 0) {
+    if ((rc = fb_ensure(h, h->scratch, o_cmp + nN + 64))) return rc;
+  }
+  char* sc = (char*)h->scratch.p;
+  FskPlans& fp = g_fsk_plans[h];
+  for (int r = 0; r < n_rec; ++r) {
+    const RecPlan& p = plans[r];
+    if (p.status != FB_ST_OK) continue;
+    const int64_t N = (int64_t)p.n;
+    auto it = fp.plans.find(N);
+    if (it == fp.plans.end()) {
+      if (fp.plans.size() >= 8) {                          // bounded plan cache
+        for (auto& q : fp.plans) { cufftDestroy(q.second.first); cufftDestroy(q.second.second); }
+        fp.plans.clear();
+      }
+      cufftHandle a, b;
+      if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2Z, 1) != CUFFT_SUCCESS) {
+        h->err = "cufftPlan1d failed";
+        return FB_ECUDA;
+      }
+      cufftSetStream(a, h->stream); cufftSetStream(b, h->stream);
+      it = fp.plans.emplace(N, std::make_pair(a, b)).first;
+    }
+    uint32_t* d_words = (uint32_t*)h->bits.p + p.word_off;
+    double* yfwd = (double*)sc; double* f = (double*)(sc + o_f);
+    cufftDoubleComplex* X = (cufftDoubleComplex*)(sc + o_X); cufftDoubleComplex* Z = (cufftDoubleComplex*)(sc + o_Z);
+    double* env = (double*)(sc + o_env); uint8_t* cmp = (uint8_t*)(sc + o_cmp);
+    if (dtype == FB_F32) rc = fsk_one<float>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
+    else if (dtype == FB_F64) rc = fsk_one<double>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
+    else rc = fsk_one<int16_t>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
+    if (rc) return rc;
+  }
+  rc = fb_bits_backend(h, n_rec, (const RecPlan*)h->plans.p, plans, 1, (const uint32_t*)h->bits.p, d_out, d_out_len, d_sync, d_status);
+  if (rc) return rc;
+  if (!(flags & FB_OUT_ON_DEVICE)) {
+    if (total_out) FB_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)total_out, cudaMemcpyDeviceToHost, h->stream));
+    FB_CUDA(h, cudaMemcpyAsync(out_len, d_out_len, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, h->stream));
+    FB_CUDA(h, cudaMemcpyAsync(sync_idx, d_sync, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, h->stream));
+    FB_CUDA(h, cudaMemcpyAsync(status, d_status, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  h->last_plans = plans;
+  h->last_bps = 1;
+  if (!(flags & FB_ASYNC) || !(flags & FB_OUT_ON_DEVICE)) FB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FB_OK;
+}

@@ -108,6 +108,20 @@ int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* d, const float* taps, 
  * (MSB-first packed, recording r at byte offset bit_offsets[r], n_bits[r] valid bits).  Host buffers. */
 int fb_psk_last_bits(fb_handle* h, int rec, uint8_t* bits_out, uint64_t cap_bytes, uint64_t* n_bits);
 
+/* ---- v2 FSK: replaces fsk_demodulate (modem.py:298-341) and its aliases fsk_high_speed_demodulate / ft8_demodulate
+ * (modem.py:355,391) for tone sets whose Butterworth design is valid (every product default raises ValueError in the
+ * host wrapper, exactly as scipy does in the reference).  tone 0 = mark, tone 1 = space.                           */
+typedef struct fb_fsk_design {
+  int32_t spb, pad;                  /* int(fs/baud); filtfilt padlen = 3*max(len(a),len(b)) = 21                    */
+  int32_t w[2];                      /* warm-up samples per tone (pole decay to 1e-12)                               */
+  double  b[2][7], a[2][7], zi[2][6];/* butter(3, [(f-baud)/nyq, (f+baud)/nyq], 'band') and lfilter_zi (modem.py:307) */
+} fb_fsk_design;
+uint64_t fb_fsk_out_bound(const fb_fsk_design* d, uint64_t n_samples);
+/* Same calling convention as fb_psk_demod_batch. */
+int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* d, int n_rec, const void* samples, const uint64_t* offsets,
+                       int dtype, int flags, uint8_t* out, const uint64_t* out_offsets,
+                       uint64_t* out_len, int64_t* sync_idx, int32_t* status);
+
 /* ---- fec.py decode (standalone ops: the reference never wires FEC into decode_from_buffer) ------------------
  * Blocks are independent; block i is in[in_offsets[i] .. in_offsets[i+1]), its slot out[out_offsets[i] ..
  * out_offsets[i+1]) (size it with fb_*_out_bound).  in_offsets / out_offsets are HOST arrays of n_blk+1 entries;
