@@ -19,7 +19,7 @@ SYMBOLS = [
     "fb_abi_version", "fb_device_count", "fb_strerror", "fb_last_error", "fb_create", "fb_destroy", "fb_stream",
     "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
     "fb_rs_out_bound", "fb_viterbi_out_bound", "fb_rs_decode_batch", "fb_viterbi_decode_batch", "fb_crc32_batch",
-    "fb_parse_frames_batch", "fb_fsk_out_bound", "fb_fsk_demod_batch",
+    "fb_parse_frames_batch", "fb_fsk_out_bound", "fb_fsk_demod_batch", "fb_v1_out_bound", "fb_v1_demod_batch",
 ]
 
 
@@ -89,6 +89,10 @@ def load() -> ctypes.CDLL:
     lib.fb_fsk_out_bound.argtypes = [vp, c.c_uint64]
     lib.fb_fsk_demod_batch.restype = c.c_int
     lib.fb_fsk_demod_batch.argtypes = [vp, vp, c.c_int, vp, u64p, c.c_int, c.c_int, u8p, u64p, vp, vp, vp]
+    lib.fb_v1_out_bound.restype = c.c_uint64
+    lib.fb_v1_out_bound.argtypes = [vp, c.c_uint64]
+    lib.fb_v1_demod_batch.restype = c.c_int
+    lib.fb_v1_demod_batch.argtypes = [vp, vp, vp, c.c_int, vp, u64p, c.c_int, c.c_int, u8p, u64p, vp, vp]
     _lib = lib
     return lib
 

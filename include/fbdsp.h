@@ -122,6 +122,25 @@ int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* d, int n_rec, const vo
                        int dtype, int flags, uint8_t* out, const uint64_t* out_offsets,
                        uint64_t* out_len, int64_t* sync_idx, int32_t* status);
 
+/* ---- "v1" streaming demodulators (present in the reference only as __pycache__/modem.cpython-39.pyc;
+ * these are the north_star's named kernels -- Goertzel tone bank, I/Q integrate-and-dump, 8PSK slicer, per-symbol DFT OFDM
+ * demap.  Parity is against oracle/modem_v1.py, which no reference test pins).  Per symbol k the kernel evaluates
+ * F_m = sum_{j<len} x[k*sps + off0 + j] * table[m][j] (complex float64 weights) and applies the mode's hard decision.   */
+enum { FB_V1_BPSK = 0, FB_V1_QPSK = 1, FB_V1_PSK8 = 2, FB_V1_OFDM = 3, FB_V1_FSK = 4 };
+typedef struct fb_v1_params {
+  int32_t mode, sps, off0, len;      /* sps = int(round(fs/baud)); OFDM: off0 = sps/4 (cyclic prefix), len = sps - off0   */
+  int32_t nf, bits_per_sym;          /* correlators per symbol (1; OFDM: bins; FSK: 2) and decided bits per symbol        */
+  int32_t uart, prefilter;           /* FSK: UART deframe (B.2) / Butterworth-4 zero-phase band-pass before Goertzel (B.1) */
+  int32_t bp_w, bp_pad;              /* pre-filter warm-up (pole decay to 1e-12) and filtfilt padlen                       */
+  double  bp_b[9], bp_a[9], bp_zi[8];
+} fb_v1_params;
+uint64_t fb_v1_out_bound(const fb_v1_params* p, uint64_t n_samples);
+/* table: HOST, nf*len complex float64 (re, im interleaved).  out slots must be 4-byte aligned.  No sync search in v1:
+ * out_len[r] = floor(bits/8) (or the UART-deframed byte count).                                                         */
+int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* p, const double* table, int n_rec, const void* samples,
+                      const uint64_t* offsets, int dtype, int flags, uint8_t* out, const uint64_t* out_offsets,
+                      uint64_t* out_len, int32_t* status);
+
 /* ---- fec.py decode (standalone ops: the reference never wires FEC into decode_from_buffer) ------------------
  * Blocks are independent; block i is in[in_offsets[i] .. in_offsets[i+1]), its slot out[out_offsets[i] ..
  * out_offsets[i+1]) (size it with fb_*_out_bound).  in_offsets / out_offsets are HOST arrays of n_blk+1 entries;

@@ -1,0 +1,97 @@
+"""-m gpu: the v1 streaming kernels against oracle/modem_v1.py (SURVEY Appendix B restatement; PARITY UNPINNED --
+no executable reference exists for v1, so these tests pin the kernels to the restatement only)."""
+import numpy as np
+import pytest
+
+from oracle import modem_v1 as v1
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(raw):
+    return np.unpackbits(np.frombuffer(raw, dtype=np.uint8))
+
+
+def _check(got_raw, st, margin_per_sym, bps):
+    want_bits = st["bits"][: (len(st["bits"]) // 8) * 8]
+    got_bits = _bits(got_raw)
+    assert len(got_bits) == len(want_bits)
+    bad = np.nonzero(got_bits != want_bits)[0]
+    assert len(bad) <= 1e-4 * max(1, len(want_bits))
+    for b in bad:
+        assert margin_per_sym[b // bps] < 1e-5
+    if len(bad) == 0:
+        assert got_raw == st["raw"]
+
+
+def _psk_signal(bps, baud, carrier, nsym, snr_db, seed):
+    """cos-referenced PSK at sector centres + AWGN (the v1 TX itself is sin-referenced and never round-tripped)."""
+    rng = np.random.default_rng(seed)
+    sps = int(round(96000 / baud))
+    t = np.arange(sps) / 96000
+    m = 2 ** bps
+    ph = rng.integers(0, m, nsym) * (2 * np.pi / m) + (np.pi / m if bps > 1 else 0.0)
+    x = np.cos(2 * np.pi * carrier * t[None, :] - ph[:, None]).reshape(-1)
+    x = x + rng.standard_normal(len(x)) * np.sqrt(0.5 / 10 ** (snr_db / 10))
+    return np.concatenate([x, rng.standard_normal(7) * 0.1]).astype(np.float32)      # ragged tail
+
+
+@pytest.mark.parametrize("baud,carrier,snr", [(9600, 9600.0, 10), (1200, 3000.0, 5), (38400, 12000.0, 10), (2400, 12000.0, 0)])
+def test_v1_qpsk(baud, carrier, snr, engine):
+    from fbdsp import modem_v1 as g
+    x = _psk_signal(2, baud, carrier, 40000 if baud >= 9600 else 4000, snr, baud)
+    st = v1.qpsk_stages(x, baud, carrier)
+    mag = np.hypot(st["i"], st["q"])
+    margin = np.minimum(np.abs(st["i"]), np.abs(st["q"])) / np.where(mag > 0, mag, 1)
+    _check(g.qpsk_demodulate(x, baud, carrier), st, margin, 2)
+
+
+def test_v1_bpsk_and_8psk(engine):
+    from fbdsp import modem_v1 as g
+    x = _psk_signal(1, 9600, 3000.0, 30000, 10, 1)
+    st = v1.bpsk_stages(x, 9600, 3000.0)
+    _check(g.bpsk_demodulate(x, 9600, 3000.0), st, np.abs(st["i"]) / np.maximum(np.hypot(st["i"], st["q"]), 1e-300), 1)
+    x = _psk_signal(3, 2400, 12000.0, 9000, 15, 2)
+    st = v1.psk8_stages(x, 2400, 12000.0)
+    thr = np.array([1, 3, 5, 7, 9, 11, 13, 16]) * np.pi / 8        # sector edges (0/2pi is not an edge: '111' wraps)
+    margin = np.min(np.abs(st["phi"][:, None] - thr[None, :]), axis=1) / (np.pi / 8)
+    _check(g.psk8_demodulate(x, 2400, 12000.0), st, margin, 3)
+
+
+@pytest.mark.parametrize("baud,nsub", [(9600, 8), (9600, 4), (4800, 8), (2400, 4)])
+def test_v1_ofdm(baud, nsub, engine):
+    from fbdsp import modem_v1 as g
+    rng = np.random.default_rng(baud + nsub)
+    x = rng.standard_normal(300000 + 3)                           # float64 stays float64 (B.7 has no cast)
+    st = v1.ofdm_stages(x, baud, 12000.0, nsub)
+    sc = st["sc"].reshape(-1)
+    margin = np.minimum(np.abs(sc.real), np.abs(sc.imag)) / np.abs(sc)
+    _check(g.ofdm_demodulate_simple(x, baud, 12000.0, nsub), st, margin, 2)
+    assert g.ofdm_demodulate_simple(x.astype(np.float32), baud, 12000.0, nsub) == v1.ofdm_demodulate_simple(x.astype(np.float32), baud, 12000.0, nsub)
+
+
+def test_v1_fsk_uart_roundtrip_and_hs(engine):
+    from fbdsp import modem_v1 as g
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 700, dtype=np.uint8).tobytes()
+    x = v1.fsk_modulate(data, 1200)
+    x = (x + rng.standard_normal(len(x)).astype(np.float32) * np.float32(0.05)).astype(np.float32)
+    st = v1.fsk_stages(x, 1200)
+    got = g.fsk_demodulate(x, 1200)
+    assert got == st["raw"] == data                                # v1 FSK1200 does round-trip (UART framing)
+    x = (rng.standard_normal(200001) * 0.3).astype(np.float32)     # FSK-HS on noise: decisions vs the restatement
+    st = v1.fsk_high_speed_stages(x)
+    margin = np.abs(st["p_mark"] - st["p_space"]) / np.maximum(st["p_mark"], st["p_space"])
+    _check(g.fsk_high_speed_demodulate(x), st, margin, 1)
+    with pytest.raises(ValueError):
+        g.fsk_demodulate(np.zeros(20, np.float32), 1200)
+
+
+def test_v1_ragged_batch(engine):
+    from fbdsp import modem_v1 as g
+    p, table = g.psk_params(g.V1_QPSK, 9600, 9600.0)
+    recs = [_psk_signal(2, 9600, 9600.0, n, 12, 50 + n) for n in (1, 7, 256, 257, 5000, 0)]
+    recs[-1] = np.zeros(3, np.float32)                             # fewer samples than one symbol -> b''
+    out = g.demod_batch(recs, p, table, engine)
+    for x, (raw, st) in zip(recs, out):
+        assert raw == v1.qpsk_demodulate(x, 9600, 9600.0)
