@@ -20,30 +20,33 @@
 #include <algorithm>
 #include <math.h>
 
-#define MAIN_S 4             // symbols per thread in the FIR phase
-#define SLOW_CH 5            // columns per thread in the slow-pole phase (odd: conflict-free LDS)
+#define PM_CH 8              // columns (= symbols) per thread: FIR register tile and slow-pole scan chunk
+#define PM_THREADS 256
+#define PM_MAXTAB 3712       // float2 entries of the per-launch constant table (taps + slow-pole row weights)
 #define SLOW_TBL 48          // per pole pair: 32 lane powers, 5 warp-scan multipliers, 9 warp powers (float2 each)
 
+// Per-launch arguments live in the kernel parameter space (constant bank 0): the FIR taps and the slow-pole row
+// weights are read as FFMA2 uniform-register operands (LDCU.64 c[0x0][..]), so the inner loop has no tap loads
+// through the LSU and nothing is shared between handles / streams.
 struct PskMainArgs {
   const void* samples;
   const RecPlan* plans;
   const uint32_t* tile_first;   // n_rec + 1 prefix of main tiles
-  const float2* taps_r;         // [sps][nt] reversed tap order
-  const float4* slow_wc;        // [nslow][sps]  {p^(sps-j), p^j}: forward / backward feature weights of row j
-  const float2* slow_pw;        // [nslow][wlen + 1]  p^k: weights of the tile-boundary state sums
-  const float2* slow_tbl;       // [nslow][SLOW_TBL]  powers of lam = p^sps used by the column scan
+  const float2* slow_pw;        // [nslow][wlen + 1]  p^k: weights of the tile-boundary state sums (global)
+  const float2* slow_tbl;       // [nslow][SLOW_TBL]  powers of m = lam^PM_CH used by the column scan (global)
   uint32_t* bits;
   int n_rec;
-  int sps, n0, bps, nt, dl, dh, nslow, wlen, pad_bp;
+  int sps, n0, bps, nt, ntp, dl, dh, nslow, wlen, pad_bp;
   int T;                        // tile size in differential symbols (multiple of 32)
   int P;                        // shared-memory row pitch in floats (multiple of 4)
-  int rg;                       // row groups (threads cooperating on one symbol chunk)
-  int right;                    // columns staged right of the last tile symbol
+  int padl;                     // columns staged left of (d0 - dh): makes the centre column 16-byte aligned
+  int wc_off;                   // tab[wc_off + (i*sps + j)*2 + {0,1}] = {p_i^(sps-j), p_i^j}
   float2 rho;
-  float2 lam[FB_MAX_SLOW];
+  float2 lam[FB_MAX_SLOW];      // p^sps
   // R F + R' conj(F) as a real 2x2 map of (Re F, Im F): {a11, a12, a21, a22}; af = forward, ab = backward residues
   float4 af[FB_MAX_SLOW], ab[FB_MAX_SLOW];
   double slow_p[2 * FB_MAX_SLOW];
+  float2 tab[PM_MAXTAB];        // [sps][ntp] reversed taps, then the slow-pole row weights
 };
 
 // 4 consecutive samples starting at element index i (i and the base pointer aligned to 4 elements)
@@ -62,66 +65,31 @@ template <> __device__ __forceinline__ float4 load4<int16_t>(const void* base, u
   return make_float4((float)v.x * k, (float)v.y * k, (float)v.z * k, (float)v.w * k);
 }
 
-// Register-tiled polyphase FIR over the rows j = g, g+rg, ... of one symbol chunk.
-//   acc[s] += taps_r[j][t'] * X[j][base + s + t']      s < S, t' < nt (nt even: one LDS.128 = two complex taps)
-// NTH > 0: tap-pair count known at compile time (window fully in registers); NTH == 0: runtime loop.
-template <int S, int NTH>
-__device__ __forceinline__ void fir_rows(const float* X, const float2* taps, int P, int nt, int sps, int g, int rg,
-                                         int base, float (&accr)[S], float (&acci)[S]) {
-  for (int j = g; j < sps; j += rg) {
-    const float4* row = reinterpret_cast<const float4*>(X + (size_t)j * P + base);
-    const float4* tp = reinterpret_cast<const float4*>(taps + (size_t)j * nt);
-    if (NTH > 0) {
-      constexpr int NW = (2 * NTH + S - 1 + 3) / 4;           // float4 loads covering nt + S - 1 columns
-      float win[4 * NW];
-#pragma unroll
-      for (int q = 0; q < NW; ++q) {
-        const float4 v = row[q];
-        win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int th = 0; th < NTH; ++th) {
-        const float4 t01 = tp[th];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          accr[s] = fmaf(t01.x, win[2 * th + s], accr[s]);     acci[s] = fmaf(t01.y, win[2 * th + s], acci[s]);
-          accr[s] = fmaf(t01.z, win[2 * th + s + 1], accr[s]); acci[s] = fmaf(t01.w, win[2 * th + s + 1], acci[s]);
-        }
-      }
-    } else {
-      float win[S + 4];
-#pragma unroll
-      for (int q = 0; q < S / 4; ++q) {
-        const float4 v = row[q];
-        win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
-      }
-      const int nth = nt / 2;
-      for (int th = 0; th < nth; th += 2) {                    // two tap pairs per step (second may be absent)
-        const float4 v = row[th / 2 + S / 4];
-        win[S] = v.x; win[S + 1] = v.y; win[S + 2] = v.z; win[S + 3] = v.w;
-        const float4 t01 = tp[th];
-        const float4 t23 = (th + 1 < nth) ? tp[th + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          accr[s] = fmaf(t01.x, win[s], accr[s]);     acci[s] = fmaf(t01.y, win[s], acci[s]);
-          accr[s] = fmaf(t01.z, win[s + 1], accr[s]); acci[s] = fmaf(t01.w, win[s + 1], acci[s]);
-          accr[s] = fmaf(t23.x, win[s + 2], accr[s]); acci[s] = fmaf(t23.y, win[s + 2], acci[s]);
-          accr[s] = fmaf(t23.z, win[s + 3], accr[s]); acci[s] = fmaf(t23.w, win[s + 3], acci[s]);
-        }
-#pragma unroll
-        for (int s = 0; s < S; ++s) win[s] = win[s + 4];
-      }
-    }
-  }
+// packed fp32 pairs (FFMA2 on sm_100a): a complex accumulator is one 64-bit register pair
+__device__ __forceinline__ float2 bfma(float x, float2 w, float2 acc) {       // acc + x * w   (x broadcast)
+  return __ffma2_rn(make_float2(x, x), w, acc);
+}
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 c) {        // a*b + c  (complex)
+  return bfma(b.y, make_float2(-a.y, a.x), bfma(b.x, a, c));
+}
+__device__ __forceinline__ float2 map22(float4 m, float fr, float fi, float2 acc) {   // acc + [m.x m.y; m.z m.w] (fr, fi)
+  return bfma(fi, make_float2(m.y, m.w), bfma(fr, make_float2(m.x, m.z), acc));
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(FB_THREADS, 3) psk_main_kernel(const PskMainArgs a) {
+// NT > 0: taps per polyphase row known at compile time (14 / 16 / 18: the window of NT + 7 columns lives in registers
+// and every tap index is an immediate offset into the parameter bank); NT == 0: runtime nt (rows padded to ntp % 4 == 0).
+template <typename TIn, int NT>
+__global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float2 s_bnd[2][4][2];      // boundary-state partial sums [dir][slice][pole of the pair]
+  __shared__ float2 s_tot[8][4];         // warp totals of the column scan [warp][seq]
+  __shared__ float2 s_car[8][4];         // state entering each warp [warp][seq]
+  __shared__ float2 s_y0[9];             // y of each warp's first symbol (differential across warp edges)
+  __shared__ double finit_sh[2 * FB_MAX_SLOW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
   const int sps = a.sps;
-  // ---- which recording / tile -----------------------------------------------------------------
-  // largest r with tile_first[r] <= tile: 32-way splitter search (two dependent loads for up to 1024 recordings)
+  constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
+  // ---- which recording / tile: largest r with tile_first[r] <= tile (32-way splitter search) -------------
   const uint32_t tile = blockIdx.x;
   int lo = 0, hi = a.n_rec;
   while (hi - lo > 1) {
@@ -134,53 +102,45 @@ __global__ void __launch_bounds__(FB_THREADS, 3) psk_main_kernel(const PskMainAr
     lo = nlo;
   }
   const RecPlan pl = a.plans[lo];
-  const int d0 = pl.dl32 + (int)(tile - a.tile_first[lo]) * a.T;
+  const int d0 = pl.dl32 + (int)(tile - __ldg(&a.tile_first[lo])) * a.T;
   const int d1 = min(d0 + a.T, pl.dr32);
   const int ns = d1 - d0 + 1;                       // symbols d0 .. d1
   const int64_t N = (int64_t)pl.n;
-  // ---- shared memory carve-up -----------------------------------------------------------------
-  float* X = smem;                                  // [sps][P]
-  float2* taps = reinterpret_cast<float2*>(X + (size_t)sps * a.P);      // [sps][nt]
-  float4* wc = reinterpret_cast<float4*>(taps + (size_t)sps * a.nt);     // [nslow][sps]
-  float2* Y = reinterpret_cast<float2*>(wc + (size_t)max(1, a.nslow) * sps);   // [T + 4] slow contribution, then y'
-  float2* red = Y + (a.T + 4);                      // [8 warps][4] partials, [8][4] warp carries, [4] boundary states x2
-  __shared__ double finit_sh[2 * FB_MAX_SLOW];
-
-  const int ca = d0 - a.dh;                         // first staged column (global column == symbol index)
-  const int ncols = (d1 + a.right) - ca + 1;
+  float* X = smem;                                  // [sps][P]   X[j][c] = x[n0 + (ca + c) sps + j]
+  const int P = a.P;
+  const int ca = d0 - a.dh - PADL;                  // global column (== symbol index) of staged column 0
+  const int cc = a.dh + PADL;                       // staged column of symbol d0
   const int64_t n_d0 = (int64_t)a.n0 + (int64_t)d0 * sps;              // sample index of symbol d0
   const int64_t n_e1 = (int64_t)a.n0 + (int64_t)(d1 + 1) * sps;        // first sample after the tile's last column
   // ---- stage samples: thread <-> column (sps consecutive samples), conflict-free row stores ------------
   // A warp reads 32*sps consecutive samples; each 128-byte line is fetched from L2 once and re-hit in L1.
   {
     const int64_t n_a = (int64_t)a.n0 + (int64_t)ca * sps;          // sample index of staged element 0
-    for (int c = tid; c < ncols; c += FB_THREADS) {
+    const int ncols = min(P, cc + ns + a.dl + 4);
+    for (int c = tid; c < ncols; c += nthr) {
       const int64_t n = n_a + (int64_t)c * sps;
       float* dst = X + c;
       if (n >= 0 && n + sps <= N) {
         const uint64_t g = pl.off + (uint64_t)n;
         if (sizeof(TIn) == 4 && (sps & 1) == 0 && (g & 1) == 0) {  // 8-byte aligned pairs
           const float2* src = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.samples) + g);
-          const int P2 = 2 * a.P;
+          const int P2 = 2 * P;
           float* d2 = dst;
 #pragma unroll 5
           for (int j = 0; j < sps; j += 2) {
             const float2 v = __ldg(src + (j >> 1));
             d2[0] = v.x;
-            d2[a.P] = v.y;
+            d2[P] = v.y;
             d2 += P2;
           }
         } else {
-          for (int j = 0; j < sps; ++j) dst[j * a.P] = load_sample<TIn>(a.samples, g + j);
+          for (int j = 0; j < sps; ++j) dst[j * P] = load_sample<TIn>(a.samples, g + j);
         }
       } else {
         for (int j = 0; j < sps; ++j)
-          dst[j * a.P] = (n + j >= 0 && n + j < N) ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
+          dst[j * P] = (n + j >= 0 && n + j < N) ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
       }
     }
-    for (int i = tid; i < sps * a.nt; i += FB_THREADS) taps[i] = a.taps_r[i];
-    for (int i = tid; i < a.nslow * sps; i += FB_THREADS) wc[i] = a.slow_wc[i];
-    for (int i = tid; i < a.T + 4; i += FB_THREADS) Y[i] = make_float2(0.f, 0.f);
   }
   // ---- exact start state of the forward slow recursion at column 0 (left record edge) ----------
   const bool near_left = (n_d0 - a.wlen) <= (int64_t)a.n0;          // the boundary sum would reach column 0
@@ -199,237 +159,283 @@ __global__ void __launch_bounds__(FB_THREADS, 3) psk_main_kernel(const PskMainAr
       double tr = pr * sr - pi * si + xv, ti = pr * si + pi * sr;
       sr = tr; si = ti;
     }
-    // Fst = p * s
-    finit_sh[2 * tid] = pr * sr - pi * si;
+    finit_sh[2 * tid] = pr * sr - pi * si;         // Fst = p * s
     finit_sh[2 * tid + 1] = pr * si + pi * sr;
   }
+
+  // this thread's PM_CH symbols e0 .. e0+7 (global d0 + e); y accumulates the slow part, then the FIR
+  const int e0 = tid * PM_CH;
+  const bool active = e0 < ns;
+  float2 y[PM_CH];
+#pragma unroll
+  for (int i = 0; i < PM_CH; ++i) y[i] = make_float2(0.f, 0.f);
 
   // ---- slow pole pairs ------------------------------------------------------------------------------
   // y_slow[c] = sum_i  R+_i Fst_i[c] + R+'_i conj(Fst_i[c]) + R-_i Bst_i[c] + R-'_i conj(Bst_i[c])
   //   Fst[c]   = sum_{n < n_c} p^(n_c - n) x[n]      Fst[c+1] = lam Fst[c] + sum_j p^(sps-j) X[j][c]
   //   Bfull[c] = sum_{n >= n_c} p^(n - n_c) x[n]     Bfull[c] = sum_j p^j X[j][c] + lam Bfull[c+1];  Bst = Bfull - x[n_c]
   // The states at the tile boundaries (Fst[d0], Bfull[d1+1]) are direct sums over the previous / next `wlen`
-  // samples against the power table p^k (read straight from global memory: no halo staging); inside the tile
-  // the recursion runs on per-column features with a decaying scan (registers + warp shuffles).
+  // samples against the power table p^k (read straight from global memory: no halo staging, no inter-CTA
+  // dependency); inside the tile the recursion runs on per-column features z (FFMA2, weights from the parameter
+  // bank), a thread-local fold, a decaying warp-shuffle scan (up for the forward states, down for the backward
+  // ones) and a serial carry over the <= 8 warps.
   for (int pair = 0; pair < a.nslow; pair += 2) {
     const bool two = pair + 1 < a.nslow;
     const int i1 = two ? pair + 1 : pair;
     const float2 lam0 = a.lam[pair], lam1 = a.lam[i1];
-    // (1) boundary sums: index 0,1 = forward pole 0,1; 2,3 = backward pole 0,1.  Warps 0-1 take the forward sum,
-    //     warps 2-3 the backward one (4 consecutive samples per thread and step); the other warps go straight on.
-    {
-      float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
-      if (warp < 4) {
-        const float2* pw0 = a.slow_pw + (size_t)pair * (a.wlen + 1);
-        const float2* pw1 = a.slow_pw + (size_t)i1 * (a.wlen + 1);
-        const bool fwd = warp < 2;
-        const int t64 = tid & 63;
-        int cnt; int64_t nbeg; int kbeg, kstep;                 // sample n = nbeg + m has weight p^(kbeg + kstep*m)
-        if (fwd) {
-          const int64_t flo = near_left ? (int64_t)a.n0 : n_d0 - a.wlen;       // n in [flo, n_d0), weight p^(n_d0 - n)
-          cnt = (int)(n_d0 - flo); nbeg = flo; kbeg = cnt; kstep = -1;
-        } else {
-          cnt = (int)max((int64_t)0, min((int64_t)a.wlen, N - n_e1));           // n in [n_e1, n_e1 + cnt), weight p^(n - n_e1)
-          nbeg = n_e1; kbeg = 0; kstep = 1;
-        }
-        for (int m0 = 4 * t64; m0 < cnt; m0 += 256) {
-          float xv[4];
-          float2 w0[4], w1[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool ok = m0 + u < cnt;
-            const int k = kbeg + kstep * (m0 + u);
-            xv[u] = ok ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(nbeg + m0 + u)) : 0.f;
-            w0[u] = ok ? __ldg(&pw0[k]) : make_float2(0.f, 0.f);
-            w1[u] = ok ? __ldg(&pw1[k]) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            bs0.x = fmaf(w0[u].x, xv[u], bs0.x); bs0.y = fmaf(w0[u].y, xv[u], bs0.y);
-            bs1.x = fmaf(w1[u].x, xv[u], bs1.x); bs1.y = fmaf(w1[u].y, xv[u], bs1.y);
-          }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          bs0.x += __shfl_xor_sync(0xffffffffu, bs0.x, off); bs0.y += __shfl_xor_sync(0xffffffffu, bs0.y, off);
-          bs1.x += __shfl_xor_sync(0xffffffffu, bs1.x, off); bs1.y += __shfl_xor_sync(0xffffffffu, bs1.y, off);
-        }
-        if (lane == 0) { red[64 + warp * 2] = bs0; red[64 + warp * 2 + 1] = bs1; }   // [w0 f0,f1][w1 f0,f1][w2 b0,b1][w3 b0,b1]
+    // (1) boundary sums: 2 directions x 4 slices of 128 samples per step, one warp per (direction, slice) job
+    for (int job = warp; job < 8; job += nwarp) {
+      const bool fwd = job < 4;
+      const int slice = job & 3;
+      const float2* pw0 = a.slow_pw + (size_t)pair * (a.wlen + 1);
+      const float2* pw1 = a.slow_pw + (size_t)i1 * (a.wlen + 1);
+      int cnt; int64_t nbeg; int kbeg, kstep;                 // sample n = nbeg + m has weight p^(kbeg + kstep*m)
+      if (fwd) {
+        const int64_t flo = near_left ? (int64_t)a.n0 : n_d0 - a.wlen;       // n in [flo, n_d0), weight p^(n_d0 - n)
+        cnt = (int)(n_d0 - flo); nbeg = flo; kbeg = cnt; kstep = -1;
+      } else {
+        cnt = (int)max((int64_t)0, min((int64_t)a.wlen, N - n_e1));           // n in [n_e1, n_e1 + cnt), weight p^(n - n_e1)
+        nbeg = n_e1; kbeg = 0; kstep = 1;
       }
+      float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
+      for (int m0 = 4 * (slice * 32 + lane); m0 < cnt; m0 += 512) {
+        float xv[4];
+        float2 w0[4], w1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = m0 + u < cnt;
+          const int k = kbeg + kstep * (m0 + u);
+          xv[u] = ok ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(nbeg + m0 + u)) : 0.f;
+          w0[u] = ok ? __ldg(&pw0[k]) : make_float2(0.f, 0.f);
+          w1[u] = ok ? __ldg(&pw1[k]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { bs0 = bfma(xv[u], w0[u], bs0); bs1 = bfma(xv[u], w1[u], bs1); }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        bs0.x += __shfl_xor_sync(0xffffffffu, bs0.x, off); bs0.y += __shfl_xor_sync(0xffffffffu, bs0.y, off);
+        bs1.x += __shfl_xor_sync(0xffffffffu, bs1.x, off); bs1.y += __shfl_xor_sync(0xffffffffu, bs1.y, off);
+      }
+      if (lane == 0) { s_bnd[fwd ? 0 : 1][slice][0] = bs0; s_bnd[fwd ? 0 : 1][slice][1] = bs1; }
     }
-    if (pair == 0) __syncthreads();                   // staged samples (and finit) visible
-    // (2) per-column features of this thread's SLOW_CH columns (scan index e: forward column d0 + e, backward d1 - e)
-    const int e0 = tid * SLOW_CH;
-    float2 z[4][SLOW_CH];
+    __syncthreads();                                  // staged samples, finit and the boundary sums are visible
+    // (2) per-column features of this thread's columns: z[0],z[1] forward (pole 0,1), z[2],z[3] backward
+    float2 z[4][PM_CH];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int i = 0; i < SLOW_CH; ++i) z[k][i] = make_float2(0.f, 0.f);
-    if (e0 < ns) {
-      // columns d0 + e0 + i (forward) and d1 - e0 - i (backward): contiguous, so one base address each and
-      // immediate offsets; columns past the tile are staged halo / zero and are discarded just below
-      const float4* w0p = wc + (size_t)pair * sps;
-      const float4* w1p = wc + (size_t)i1 * sps;
-      const float* rf = X + (d0 + e0 - ca);
-      const float* rb = X + (d1 - e0 - ca);
+      for (int i = 0; i < PM_CH; ++i) z[k][i] = make_float2(0.f, 0.f);
+    float x0c[PM_CH];                                 // x[n_c] of the thread's columns (row 0)
+#pragma unroll
+    for (int i = 0; i < PM_CH; ++i) x0c[i] = 0.f;
+    if (active) {
+      const float* rf = X + cc + e0;
+      const float2* w0p = a.tab + a.wc_off + (size_t)pair * sps * 2;
+      const float2* w1p = a.tab + a.wc_off + (size_t)i1 * sps * 2;
       for (int j = 0; j < sps; ++j) {
-        const float4 w0 = w0p[j], w1 = w1p[j];
+        float xs[PM_CH];
+        if (NT) {
+          const float4 u0 = *reinterpret_cast<const float4*>(rf), u1 = *reinterpret_cast<const float4*>(rf + 4);
+          xs[0] = u0.x; xs[1] = u0.y; xs[2] = u0.z; xs[3] = u0.w; xs[4] = u1.x; xs[5] = u1.y; xs[6] = u1.z; xs[7] = u1.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < SLOW_CH; ++i) {
-          const float xf = rf[i], xb = rb[-i];
-          z[0][i].x = fmaf(w0.x, xf, z[0][i].x); z[0][i].y = fmaf(w0.y, xf, z[0][i].y);
-          z[1][i].x = fmaf(w1.x, xf, z[1][i].x); z[1][i].y = fmaf(w1.y, xf, z[1][i].y);
-          z[2][i].x = fmaf(w0.z, xb, z[2][i].x); z[2][i].y = fmaf(w0.w, xb, z[2][i].y);
-          z[3][i].x = fmaf(w1.z, xb, z[3][i].x); z[3][i].y = fmaf(w1.w, xb, z[3][i].y);
+          for (int i = 0; i < PM_CH; ++i) xs[i] = rf[i];
         }
-        rf += a.P; rb += a.P;
-      }
+        if (j == 0) {
 #pragma unroll
-      for (int i = 0; i < SLOW_CH; ++i)
+          for (int i = 0; i < PM_CH; ++i) x0c[i] = xs[i];
+        }
+        const float2 wf0 = w0p[2 * j], wb0 = w0p[2 * j + 1], wf1 = w1p[2 * j], wb1 = w1p[2 * j + 1];
+#pragma unroll
+        for (int i = 0; i < PM_CH; ++i) {
+          z[0][i] = bfma(xs[i], wf0, z[0][i]);
+          z[1][i] = bfma(xs[i], wf1, z[1][i]);
+          z[2][i] = bfma(xs[i], wb0, z[2][i]);
+          z[3][i] = bfma(xs[i], wb1, z[3][i]);
+        }
+        rf += P;
+      }
+      // columns past the tile contribute nothing; the backward boundary state enters at the last column:
+      // Bfull[ns-1] = zb[ns-1] + lam Bfull[ns]
+      const float2 bb0 = make_float2(s_bnd[1][0][0].x + s_bnd[1][1][0].x + s_bnd[1][2][0].x + s_bnd[1][3][0].x,
+                                     s_bnd[1][0][0].y + s_bnd[1][1][0].y + s_bnd[1][2][0].y + s_bnd[1][3][0].y);
+      const float2 bb1 = make_float2(s_bnd[1][0][1].x + s_bnd[1][1][1].x + s_bnd[1][2][1].x + s_bnd[1][3][1].x,
+                                     s_bnd[1][0][1].y + s_bnd[1][1][1].y + s_bnd[1][2][1].y + s_bnd[1][3][1].y);
+      const float2 inj0 = cfma2(lam0, bb0, make_float2(0.f, 0.f)), inj1 = cfma2(lam1, bb1, make_float2(0.f, 0.f));
+#pragma unroll
+      for (int i = 0; i < PM_CH; ++i) {
         if (e0 + i >= ns) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) z[k][i] = make_float2(0.f, 0.f);
         }
+        if (e0 + i == ns - 1) {
+          z[2][i].x += inj0.x; z[2][i].y += inj0.y;
+          z[3][i].x += inj1.x; z[3][i].y += inj1.y;
+        }
+      }
     }
-    // (3) decaying scan: thread totals -> warp shuffle scan -> warp carries (warp 0) -> per-column states
+    // (3) thread totals -> warp scan (shuffle up: forward, shuffle down: backward) -> serial carry over warps
     const float2* tb0 = a.slow_tbl + (size_t)pair * SLOW_TBL;
     const float2* tb1 = a.slow_tbl + (size_t)i1 * SLOW_TBL;
     float2 v[4];
+    {
+      float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 lam = (k & 1) ? lam1 : lam0;
-      float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < SLOW_CH; ++i) s = cfma(lam, s, z[k][i]);
-      v[k] = s;
+      for (int i = 0; i < PM_CH; ++i) {
+        s0 = cfma2(lam0, s0, z[0][i]);
+        s1 = cfma2(lam1, s1, z[1][i]);
+        s2 = cfma2(lam0, s2, z[2][PM_CH - 1 - i]);
+        s3 = cfma2(lam1, s3, z[3][PM_CH - 1 - i]);
+      }
+      v[0] = s0; v[1] = s1; v[2] = s2; v[3] = s3;
     }
 #pragma unroll
     for (int st = 0; st < 5; ++st) {
-      const float2 m0 = __ldg(&tb0[32 + st]), m1 = __ldg(&tb1[32 + st]);   // (lam^CH)^(2^st)
+      const float2 m0 = __ldg(&tb0[32 + st]), m1 = __ldg(&tb1[32 + st]);   // m^(2^st), m = lam^PM_CH
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float ox = __shfl_up_sync(0xffffffffu, v[k].x, 1 << st), oy = __shfl_up_sync(0xffffffffu, v[k].y, 1 << st);
-        if (lane >= (1 << st)) v[k] = cfma((k & 1) ? m1 : m0, make_float2(ox, oy), v[k]);
+        const float2 mm = (k & 1) ? m1 : m0;
+        if (k < 2) {
+          const float ox = __shfl_up_sync(0xffffffffu, v[k].x, 1 << st), oy = __shfl_up_sync(0xffffffffu, v[k].y, 1 << st);
+          if (lane >= (1 << st)) v[k] = cfma2(mm, make_float2(ox, oy), v[k]);
+        } else {
+          const float ox = __shfl_down_sync(0xffffffffu, v[k].x, 1 << st), oy = __shfl_down_sync(0xffffffffu, v[k].y, 1 << st);
+          if (lane + (1 << st) < 32) v[k] = cfma2(mm, make_float2(ox, oy), v[k]);
+        }
       }
     }
-    if (lane == 31) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) red[warp * 4 + k] = v[k];
-    }
+    if (lane == 31) { s_tot[warp][0] = v[0]; s_tot[warp][1] = v[1]; }
+    if (lane == 0) { s_tot[warp][2] = v[2]; s_tot[warp][3] = v[3]; }
     __syncthreads();
-    if (warp == 0) {                                  // lane = 4 w + k: carry entering warp w for sequence k
-      const int k = lane & 3, w = lane >> 2;
+    if (tid < 4) {
+      const int k = tid;
       const float2* tb = (k & 1) ? tb1 : tb0;
-      float2 t = red[lane];                           // total of warp w (zero start)
-#pragma unroll
-      for (int st = 0; st < 3; ++st) {                // inclusive scan over w with multiplier M^(2^st), M = lam^(32 CH)
-        const float2 mm = __ldg(&tb[37 + (1 << st)]); // M^1, M^2, M^4
-        const float ox = __shfl_up_sync(0xffffffffu, t.x, 4 << st), oy = __shfl_up_sync(0xffffffffu, t.y, 4 << st);
-        if (w >= (1 << st)) t = cfma(mm, make_float2(ox, oy), t);
-      }
-      const float ex = __shfl_up_sync(0xffffffffu, t.x, 4), ey = __shfl_up_sync(0xffffffffu, t.y, 4);
-      float2 cin = (w > 0) ? make_float2(ex, ey) : make_float2(0.f, 0.f);
-      // boundary state of sequence k (0,1 = forward pole 0,1; 2,3 = backward): two warp partials (+ the exact left start)
-      const int q = 64 + (k >> 1) * 4 + (k & 1);
-      float2 bnd = make_float2(red[q].x + red[q + 2].x, red[q].y + red[q + 2].y);
-      if (k < 2 && near_left) {                       // + p^(n_d0 - n0) Fst[0]
-        const int i = (k == 0) ? pair : i1;
-        const float2 pw = __ldg(&a.slow_pw[(size_t)i * (a.wlen + 1) + (int)(n_d0 - a.n0)]);
-        bnd = cfma(pw, make_float2((float)finit_sh[2 * i], (float)finit_sh[2 * i + 1]), bnd);
-      }
-      cin = cfma(__ldg(&tb[37 + w]), bnd, cin);       // + M^w * boundary state
-      red[32 + lane] = cin;
-    }
-    __syncthreads();
-    float2 sc[4];                                     // state entering this thread's first column
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float ex = __shfl_up_sync(0xffffffffu, v[k].x, 1), ey = __shfl_up_sync(0xffffffffu, v[k].y, 1);
-      const float2 excl = lane > 0 ? make_float2(ex, ey) : make_float2(0.f, 0.f);
-      sc[k] = cfma(__ldg(&((k & 1) ? tb1 : tb0)[lane]), red[32 + warp * 4 + k], excl);
-    }
-    if (e0 < ns) {
-      const float4 af0 = a.af[pair], af1 = a.af[i1], ab0 = a.ab[pair], ab1 = a.ab[i1];
-#pragma unroll
-      for (int i = 0; i < SLOW_CH; ++i) {
-        const int e = e0 + i;
-        if (e < ns) {                                 // forward: Fst[d0 + e] = S[e] (state before column e)
-          float ar = fmaf(af0.x, sc[0].x, af0.y * sc[0].y), ai = fmaf(af0.z, sc[0].x, af0.w * sc[0].y);
-          if (two) {
-            ar = fmaf(af1.x, sc[1].x, fmaf(af1.y, sc[1].y, ar)); ai = fmaf(af1.z, sc[1].x, fmaf(af1.w, sc[1].y, ai));
-          }
-          atomicAdd(&Y[e].x, ar); atomicAdd(&Y[e].y, ai);
+      const float2 M = __ldg(&tb[38]);                // m^32
+      if (k < 2) {                                    // state entering warp w from the left; warp 0: Fst[d0]
+        float2 c = make_float2(s_bnd[0][0][k].x + s_bnd[0][1][k].x + s_bnd[0][2][k].x + s_bnd[0][3][k].x,
+                               s_bnd[0][0][k].y + s_bnd[0][1][k].y + s_bnd[0][2][k].y + s_bnd[0][3][k].y);
+        if (near_left) {                              // + p^(n_d0 - n0) Fst[0]
+          const int i = (k == 0) ? pair : i1;
+          const float2 pw = __ldg(&a.slow_pw[(size_t)i * (a.wlen + 1) + (int)(n_d0 - a.n0)]);
+          c = cfma2(pw, make_float2((float)finit_sh[2 * i], (float)finit_sh[2 * i + 1]), c);
         }
-        sc[0] = cfma(lam0, sc[0], z[0][i]);
-        sc[1] = cfma(lam1, sc[1], z[1][i]);
-        sc[2] = cfma(lam0, sc[2], z[2][i]);
-        sc[3] = cfma(lam1, sc[3], z[3][i]);
-        if (e < ns) {                                 // backward: Bfull[d1 - e] = S[e + 1]; Bst = Bfull - x[n_col]
-          const int col = d1 - e;
-          const float x0 = X[col - ca];
-          float br = sc[2].x - x0;
-          float ar = fmaf(ab0.x, br, ab0.y * sc[2].y), ai = fmaf(ab0.z, br, ab0.w * sc[2].y);
-          if (two) {
-            br = sc[3].x - x0;
-            ar = fmaf(ab1.x, br, fmaf(ab1.y, sc[3].y, ar)); ai = fmaf(ab1.z, br, fmaf(ab1.w, sc[3].y, ai));
-          }
-          atomicAdd(&Y[col - d0].x, ar); atomicAdd(&Y[col - d0].y, ai);
-        }
+        for (int w = 0; w < nwarp; ++w) { s_car[w][k] = c; c = cfma2(M, c, s_tot[w][k]); }
+      } else {                                        // state entering warp w from the right (boundary already injected)
+        float2 c = make_float2(0.f, 0.f);
+        for (int w = nwarp - 1; w >= 0; --w) { s_car[w][k] = c; c = cfma2(M, c, s_tot[w][k]); }
       }
     }
     __syncthreads();
+    // (4) states entering this thread's chunk, then the per-column recursion and the residue maps
+    {
+      float2 sc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2* tb = (k & 1) ? tb1 : tb0;
+        float ex, ey;
+        if (k < 2) { ex = __shfl_up_sync(0xffffffffu, v[k].x, 1); ey = __shfl_up_sync(0xffffffffu, v[k].y, 1); }
+        else { ex = __shfl_down_sync(0xffffffffu, v[k].x, 1); ey = __shfl_down_sync(0xffffffffu, v[k].y, 1); }
+        const bool has = (k < 2) ? lane > 0 : lane < 31;
+        const float2 excl = has ? make_float2(ex, ey) : make_float2(0.f, 0.f);
+        sc[k] = cfma2(__ldg(&tb[(k < 2) ? lane : 31 - lane]), s_car[warp][k], excl);
+      }
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 af0 = a.af[pair], af1 = two ? a.af[i1] : z4, ab0 = a.ab[pair], ab1 = two ? a.ab[i1] : z4;
+#pragma unroll
+      for (int i = 0; i < PM_CH; ++i) {               // forward: Fst[d0 + e0 + i] is the state BEFORE column i
+        y[i] = map22(af0, sc[0].x, sc[0].y, y[i]);
+        y[i] = map22(af1, sc[1].x, sc[1].y, y[i]);
+        sc[0] = cfma2(lam0, sc[0], z[0][i]);
+        sc[1] = cfma2(lam1, sc[1], z[1][i]);
+      }
+#pragma unroll
+      for (int i = PM_CH - 1; i >= 0; --i) {          // backward: Bfull[col] includes the column; Bst = Bfull - x[n_col]
+        sc[2] = cfma2(lam0, sc[2], z[2][i]);
+        sc[3] = cfma2(lam1, sc[3], z[3][i]);
+        y[i] = map22(ab0, sc[2].x - x0c[i], sc[2].y, y[i]);
+        y[i] = map22(ab1, sc[3].x - x0c[i], sc[3].y, y[i]);
+      }
+    }
+    if (pair + 2 < a.nslow) __syncthreads();          // s_bnd / s_tot / s_car are rewritten by the next pair
   }
   if (a.nslow == 0) __syncthreads();
 
   // ---- fast part: register-tiled polyphase FIR at symbol instants --------------------------------
-  {
-    const int nchunks = (ns + MAIN_S - 1) / MAIN_S;
-    const int chunk = tid % nchunks, g = tid / nchunks;
-    if (g < a.rg) {
-      float accr[MAIN_S], acci[MAIN_S];
+  //   y[s] += tapsR[j][t'] * X[j][e0 + PADL + s + t']   -- one FFMA2 per (complex tap, real sample), taps as uniform operands
+  if (active) {
+    const float* row = X + e0;
+    if (NT) {
+      constexpr int NW = (PADL + NT + PM_CH - 1 + 3) / 4;      // float4 loads covering the window
+      const float2* tp = a.tab;
+      for (int j = 0; j < sps; ++j) {
+        float win[4 * NW];
 #pragma unroll
-      for (int s = 0; s < MAIN_S; ++s) { accr[s] = 0.f; acci[s] = 0.f; }
-      // y[s] += tapsR[j][t'] * X[j][base + s + t'],  base = chunk*S  (staging starts at column d0 - dh)
-      const int base = chunk * MAIN_S;
-      switch (a.nt / 2) {
-        case 8: fir_rows<MAIN_S, 8>(X, taps, a.P, a.nt, sps, g, a.rg, base, accr, acci); break;
-        case 9: fir_rows<MAIN_S, 9>(X, taps, a.P, a.nt, sps, g, a.rg, base, accr, acci); break;
-        case 10: fir_rows<MAIN_S, 10>(X, taps, a.P, a.nt, sps, g, a.rg, base, accr, acci); break;
-        default: fir_rows<MAIN_S, 0>(X, taps, a.P, a.nt, sps, g, a.rg, base, accr, acci); break;
-      }
-#pragma unroll
-      for (int s = 0; s < MAIN_S; ++s) {
-        const int e = chunk * MAIN_S + s;
-        if (e < ns) {
-          if (a.rg == 1) {
-            float2 y = Y[e];
-            Y[e] = make_float2(y.x + accr[s], y.y + acci[s]);
-          } else {
-            atomicAdd(&Y[e].x, accr[s]);
-            atomicAdd(&Y[e].y, acci[s]);
-          }
+        for (int q = 0; q < NW; ++q) {
+          const float4 u = reinterpret_cast<const float4*>(row)[q];
+          win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
         }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const float2 w = tp[t];
+#pragma unroll
+          for (int s = 0; s < PM_CH; ++s) y[s] = bfma(win[PADL + s + t], w, y[s]);
+        }
+        row += P;
+        tp += NT;
+      }
+    } else {
+      const float2* tp = a.tab;
+      for (int j = 0; j < sps; ++j) {
+        float win[PM_CH + 4];
+        {
+          const float4 u0 = reinterpret_cast<const float4*>(row)[0], u1 = reinterpret_cast<const float4*>(row)[1];
+          win[0] = u0.x; win[1] = u0.y; win[2] = u0.z; win[3] = u0.w; win[4] = u1.x; win[5] = u1.y; win[6] = u1.z; win[7] = u1.w;
+        }
+        for (int t4 = 0; t4 < a.ntp; t4 += 4) {
+          const float4 u = reinterpret_cast<const float4*>(row)[2 + (t4 >> 2)];
+          win[8] = u.x; win[9] = u.y; win[10] = u.z; win[11] = u.w;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 w = tp[t4 + t];
+#pragma unroll
+            for (int s = 0; s < PM_CH; ++s) y[s] = bfma(win[s + t], w, y[s]);
+          }
+#pragma unroll
+          for (int s = 0; s < PM_CH; ++s) win[s] = win[s + 4];
+        }
+        row += P;
+        tp += a.ntp;
       }
     }
   }
-  __syncthreads();
 
-  // ---- differential decisions, 32 bits per thread, big-endian words -------------------------------
+  // ---- differential decisions: PM_CH per thread, 32-bit big-endian words assembled across 2 (DQPSK) / 4 (DBPSK) lanes --
   {
-    const int dper = 32 / a.bps;                      // dsyms per word
-    const int nwords = (d1 - d0) / dper;
-    for (int wd = tid; wd < nwords; wd += FB_THREADS) {
-      uint32_t word = 0;
-      float2 prev = Y[wd * dper];
-      for (int k = 0; k < dper; ++k) {
-        const float2 cur = Y[wd * dper + k + 1];
-        // d = cur * conj(prev) * rho
-        const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
-        const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
-        word = (word << a.bps) | psk_decide<float>(dr, di, a.bps);
-        prev = cur;
-      }
-      a.bits[pl.word_off + (uint64_t)(d0 / dper) + wd] = __byte_perm(word, 0, 0x0123);
+    if (lane == 0) s_y0[warp] = y[0];
+    __syncthreads();
+    float nx = __shfl_down_sync(0xffffffffu, y[0].x, 1), nyv = __shfl_down_sync(0xffffffffu, y[0].y, 1);
+    if (lane == 31 && warp + 1 < nwarp) { nx = s_y0[warp + 1].x; nyv = s_y0[warp + 1].y; }
+    uint32_t part = 0;
+#pragma unroll
+    for (int i = 0; i < PM_CH; ++i) {
+      const float2 prev = y[i];
+      const float2 cur = (i + 1 < PM_CH) ? y[(i + 1) % PM_CH] : make_float2(nx, nyv);
+      // d = cur * conj(prev) * rho
+      const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
+      const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
+      part = (part << a.bps) | psk_decide<float>(dr, di, a.bps);
+    }
+    const int nd = d1 - d0;                           // multiple of 32
+    if (a.bps == 2) {                                 // 16 bits per thread, 2 threads per word
+      const uint32_t other = __shfl_down_sync(0xffffffffu, part, 1);
+      if ((lane & 1) == 0 && e0 < nd)
+        a.bits[pl.word_off + (uint64_t)((d0 + e0) >> 4)] = __byte_perm((part << 16) | other, 0, 0x0123);
+    } else {                                          // 8 bits per thread, 4 threads per word
+      uint32_t wv = part << (24 - 8 * (lane & 3));
+      wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
+      wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
+      if ((lane & 3) == 0 && e0 < nd) a.bits[pl.word_off + (uint64_t)((d0 + e0) >> 5)] = __byte_perm(wv, 0, 0x0123);
     }
   }
 }
@@ -664,7 +670,7 @@ static void make_job(const fb_psk_design& d, int rec, int64_t N, int k_lo, int k
 }
 
 template <typename TIn>
-static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, size_t smem, const PskEdgeArgs& ea) {
+static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int nthreads, size_t smem, const PskEdgeArgs& ea) {
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -673,9 +679,17 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, siz
     h->launches++;
   }
   if (n_tiles > 0) {
-    FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
-    psk_main_kernel<TIn><<<n_tiles, FB_THREADS, smem, h->stream>>>(ma);
+    switch (ma.nt == ma.ntp ? ma.nt : 0) {
+#define FB_LAUNCH_MAIN(NTV)                                                                                               \
+      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      psk_main_kernel<TIn, NTV><<<n_tiles, nthreads, smem, h->stream>>>(ma)
+      case 14: FB_LAUNCH_MAIN(14); break;
+      case 16: FB_LAUNCH_MAIN(16); break;
+      case 18: FB_LAUNCH_MAIN(18); break;
+      default: FB_LAUNCH_MAIN(0); break;
+#undef FB_LAUNCH_MAIN
+    }
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
   }
@@ -701,24 +715,26 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   const int bps = d.bits_per_sym, dper = 32 / bps;
 
   // ---- tile geometry of the main kernel -------------------------------------------------------------
-  int T = 0, P = 0, rg = 1, right = 0;
+  int T = 0, P = 0, nthreads = PM_THREADS, ntp = d.nt, padl = 0;
   const int wlen = d.wcols * d.sps;
   size_t smem = 0;
-  if (!d.emulate_only) {
-    if ((d.nt & 1) || d.dh < SLOW_CH - 1) return FB_EINVAL;
+  bool emulate_only = d.emulate_only != 0;
+  if (!emulate_only) {
+    if ((d.nt & 1) || d.dh != d.nt / 2 || d.dl != d.nt / 2 - 1) return FB_EINVAL;
+    const bool spec = d.nt == 14 || d.nt == 16 || d.nt == 18;      // compile-time tap count: window in registers
+    ntp = spec ? d.nt : (d.nt + 3) / 4 * 4;
+    padl = spec ? (4 - d.dh % 4) % 4 : 0;
     // the FIR windows are whole float4s: they over-read a few columns right of the last tap
-    right = d.dl + MAIN_S + 12;
-    const size_t budget = 72 * 1024;
-    for (T = std::min(FB_THREADS * MAIN_S - 32, (FB_THREADS * SLOW_CH - 1) / 32 * 32); T >= 32; T -= 32) {
-      const int ncols = T + 1 + d.dh + right;
-      P = (ncols + 3) / 4 * 4 + 4;
-      smem = (size_t)d.sps * P * 4 + (size_t)d.sps * d.nt * 8 + (size_t)std::max(1, d.nslow) * d.sps * 16 +
-             (size_t)(T + 4) * 8 + 72 * 8;
+    const int win = spec ? (padl + d.nt + PM_CH - 1 + 3) / 4 * 4 : PM_CH + ntp;
+    if ((size_t)d.sps * ntp + 2 * (size_t)std::max(1, d.nslow) * d.sps > PM_MAXTAB) emulate_only = true;   // constant table full
+    const size_t budget = 100 * 1024;                              // two CTAs per SM
+    for (T = PM_THREADS * PM_CH - 32; T >= 32; T -= 32) {
+      P = (T + 1 + PM_CH - 1) / PM_CH * PM_CH + win;
+      smem = (size_t)d.sps * P * 4;
       if (smem <= budget) break;
     }
-    if (T < 32) return FB_EUNSUPPORTED;   // design.py marks such parameter sets emulate_only
-    const int nchunks = (T + 1 + MAIN_S - 1) / MAIN_S;
-    rg = std::max(1, std::min(d.sps, FB_THREADS / nchunks));
+    if (T < 32) emulate_only = true;
+    nthreads = ((T + 1 + PM_CH - 1) / PM_CH + 31) / 32 * 32;
   }
 
   // ---- per-recording plan ---------------------------------------------------------------------------------
@@ -745,7 +761,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     if (p.nsym < 2) { p.status = FB_ST_EMPTY; p.ndsym = 0; continue; }
     words += ((uint64_t)p.ndsym * bps + 31) / 32 + 2;
     bool whole = true;
-    if (!d.emulate_only) {
+    if (!emulate_only) {
       const int64_t kmin = std::max<int64_t>(0, cdiv64((int64_t)d.zone_left - d.n0, d.sps));
       const int64_t kmax = fdiv64(N - 1 - d.zone_right - d.n0, d.sps);
       const int64_t dl32 = cdiv64(kmin, 32) * 32, dr32 = kmax >= 0 ? kmax / 32 * 32 : 0;
@@ -795,20 +811,17 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     FB_CUDA(h, cudaMemcpyAsync(h->jobs.p, jobs.data(), jobs.size() * sizeof(EdgeJob), cudaMemcpyHostToDevice, h->stream));
 
   PskMainArgs ma{};
-  if (!d.emulate_only) {
-    // reversed tap table: taps_r[j][t'] = taps[j][nt-1-t']
-    std::vector<float> tr((size_t)d.sps * d.nt * 2, 0.f);
-    for (int j = 0; j < d.sps; ++j)
-      for (int t = 0; t < d.nt; ++t) {
-        tr[((size_t)j * d.nt + t) * 2] = taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2];
-        tr[((size_t)j * d.nt + t) * 2 + 1] = taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2 + 1];
-      }
-    // slow-pole tables (float64 powers of the poles, rounded once):
-    //   wcv  [nslow][sps]       {p^(sps-j), p^j}                   per-row feature weights
+  if (!emulate_only) {
+    // constant table: reversed taps tab[j*ntp + t'] = taps[j][nt-1-t'] (zero padded to ntp), then the slow-pole row
+    // weights {p^(sps-j), p^j}.  Global tables (float64 powers of the poles, rounded once):
     //   pwv  [nslow][wlen+1]    p^k                                 tile-boundary state sums
-    //   tbl  [nslow][SLOW_TBL]  (lam^CH)^l, (lam^CH)^(2^st), M^w    scan multipliers, lam = p^sps, M = lam^(32 CH)
+    //   tbl  [nslow][SLOW_TBL]  m^l, m^(2^st), M^w                  scan multipliers, lam = p^sps, m = lam^PM_CH, M = m^32
+    ma.wc_off = d.sps * ntp;
+    for (int j = 0; j < d.sps; ++j)
+      for (int t = 0; t < d.nt; ++t)
+        ma.tab[j * ntp + t] = make_float2(taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2], taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2 + 1]);
     const int ns_ = std::max(1, d.nslow);
-    std::vector<float> wcv((size_t)ns_ * d.sps * 4, 0.f), pwv((size_t)ns_ * (wlen + 1) * 2, 0.f), tbl((size_t)ns_ * SLOW_TBL * 2, 0.f);
+    std::vector<float> pwv((size_t)ns_ * (wlen + 1) * 2, 0.f), tbl((size_t)ns_ * SLOW_TBL * 2, 0.f);
     for (int i = 0; i < d.nslow; ++i) {
       const double pr = d.slow_p[2 * i], pi = d.slow_p[2 * i + 1];
       std::vector<double> pk((size_t)(std::max(wlen, d.sps) + 1) * 2);
@@ -822,9 +835,8 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
         pwv[((size_t)i * (wlen + 1) + k) * 2 + 1] = (float)pk[2 * k + 1];
       }
       for (int j = 0; j < d.sps; ++j) {
-        float* o = &wcv[((size_t)i * d.sps + j) * 4];
-        o[0] = (float)pk[2 * (d.sps - j)]; o[1] = (float)pk[2 * (d.sps - j) + 1];
-        o[2] = (float)pk[2 * j]; o[3] = (float)pk[2 * j + 1];
+        ma.tab[ma.wc_off + (i * d.sps + j) * 2] = make_float2((float)pk[2 * (d.sps - j)], (float)pk[2 * (d.sps - j) + 1]);
+        ma.tab[ma.wc_off + (i * d.sps + j) * 2 + 1] = make_float2((float)pk[2 * j], (float)pk[2 * j + 1]);
       }
       auto cpowd = [](double br, double bi, int n, double& rr, double& ri) {
         rr = 1.0; ri = 0.0;
@@ -832,27 +844,23 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
       };
       const double lr = pk[2 * d.sps], li = pk[2 * d.sps + 1];
       double cr, ci, mr, mi, tr_, ti_;
-      cpowd(lr, li, SLOW_CH, cr, ci);                 // lam^CH
-      cpowd(cr, ci, 32, mr, mi);                      // M = lam^(32 CH)
+      cpowd(lr, li, PM_CH, cr, ci);                   // m = lam^PM_CH
+      cpowd(cr, ci, 32, mr, mi);                      // M = m^32
       float* tb = &tbl[(size_t)i * SLOW_TBL * 2];
       for (int l = 0; l < 32; ++l) { cpowd(cr, ci, l, tr_, ti_); tb[2 * l] = (float)tr_; tb[2 * l + 1] = (float)ti_; }
       for (int st = 0; st < 5; ++st) { cpowd(cr, ci, 1 << st, tr_, ti_); tb[2 * (32 + st)] = (float)tr_; tb[2 * (32 + st) + 1] = (float)ti_; }
       for (int w = 0; w < 9; ++w) { cpowd(mr, mi, w, tr_, ti_); tb[2 * (37 + w)] = (float)tr_; tb[2 * (37 + w) + 1] = (float)ti_; }
     }
-    const size_t o_wc = (tr.size() * 4 + 255) / 256 * 256, o_pw = o_wc + (wcv.size() * 4 + 255) / 256 * 256,
-                 o_tb = o_pw + (pwv.size() * 4 + 255) / 256 * 256, tab_bytes = o_tb + tbl.size() * 4;
+    const size_t o_tb = (pwv.size() * 4 + 255) / 256 * 256, tab_bytes = o_tb + tbl.size() * 4;
     if ((rc = fb_ensure(h, h->taps, tab_bytes))) return rc;
     char* tabs = (char*)h->taps.p;
-    FB_CUDA(h, cudaMemcpyAsync(tabs, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    FB_CUDA(h, cudaMemcpyAsync(tabs + o_wc, wcv.data(), wcv.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    FB_CUDA(h, cudaMemcpyAsync(tabs + o_pw, pwv.data(), pwv.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    FB_CUDA(h, cudaMemcpyAsync(tabs, pwv.data(), pwv.size() * 4, cudaMemcpyHostToDevice, h->stream));
     FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
     ma.samples = d_samples; ma.plans = (const RecPlan*)h->plans.p; ma.tile_first = (const uint32_t*)h->tile_first.p;
-    ma.taps_r = (const float2*)tabs; ma.slow_wc = (const float4*)(tabs + o_wc); ma.slow_pw = (const float2*)(tabs + o_pw);
-    ma.slow_tbl = (const float2*)(tabs + o_tb); ma.bits = (uint32_t*)h->bits.p;
-    ma.n_rec = n_rec; ma.sps = d.sps; ma.n0 = d.n0; ma.bps = bps; ma.nt = d.nt; ma.dl = d.dl; ma.dh = d.dh;
-    ma.nslow = d.nslow; ma.wlen = wlen; ma.pad_bp = d.pad_bp; ma.T = T; ma.P = P; ma.rg = rg; ma.right = right;
+    ma.slow_pw = (const float2*)tabs; ma.slow_tbl = (const float2*)(tabs + o_tb); ma.bits = (uint32_t*)h->bits.p;
+    ma.n_rec = n_rec; ma.sps = d.sps; ma.n0 = d.n0; ma.bps = bps; ma.nt = d.nt; ma.ntp = ntp; ma.dl = d.dl; ma.dh = d.dh;
+    ma.nslow = d.nslow; ma.wlen = wlen; ma.pad_bp = d.pad_bp; ma.T = T; ma.P = P; ma.padl = padl;
     ma.rho = make_float2(d.rho[0], d.rho[1]);
     for (int i = 0; i < FB_MAX_SLOW; ++i) {
       ma.lam[i] = make_float2(d.slow_lam[2 * i], d.slow_lam[2 * i + 1]);
@@ -869,9 +877,9 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   ea.samples = d_samples; ea.plans = (const RecPlan*)h->plans.p; ea.jobs = (const EdgeJob*)h->jobs.p;
   ea.scratch = (double*)h->scratch.p; ea.bits = (uint32_t*)h->bits.p; ea.n_jobs = (int)jobs.size(); ea.d = d;
 
-  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, smem, ea);
-  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, smem, ea);
-  else rc = launch_psk<int16_t>(h, ma, n_tiles, smem, ea);
+  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, nthreads, smem, ea);
+  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, nthreads, smem, ea);
+  else rc = launch_psk<int16_t>(h, ma, n_tiles, nthreads, smem, ea);
   if (rc) return rc;
 
   rc = fb_bits_backend(h, n_rec, (const RecPlan*)h->plans.p, plans, bps, (const uint32_t*)h->bits.p, d_out, d_out_len, d_sync, d_status);
