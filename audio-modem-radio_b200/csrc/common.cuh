@@ -81,11 +81,11 @@ __device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {  // a*b +
 // or the single bit for DBPSK (modem.py:105: Re(d) < 0 -> 1).
 template <typename R>
 __device__ __forceinline__ uint32_t psk_decide(R dr, R di, int bps) {
-  if (bps == 1) return dr < R(0) ? 1u : 0u;
-  R a = dr + di, b = dr - di;
-  if (a > R(0)) return (b > R(0)) ? 0u : 1u;              // 00 : 01
-  if (b < R(0)) return 3u;                                // 11
-  return (a == R(0) && b == R(0)) ? 0u : 2u;              // origin -> 00, else 10
+  const R a = dr + di, b = dr - di;
+  // a > 0: 00 | 01;  else b < 0: 11;  else origin -> 00, otherwise 10   (selects, no branches)
+  const uint32_t q = (a > R(0)) ? ((b > R(0)) ? 0u : 1u) : ((b < R(0)) ? 3u : ((a == R(0) && b == R(0)) ? 0u : 2u));
+  const uint32_t p = dr < R(0) ? 1u : 0u;
+  return bps == 1 ? p : q;
 }
 template <typename T> __device__ __forceinline__ float load_sample(const void* base, uint64_t i);
 template <> __device__ __forceinline__ float load_sample<float>(const void* base, uint64_t i) {

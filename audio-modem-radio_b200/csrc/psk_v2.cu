@@ -32,7 +32,8 @@ struct PskMainArgs {
   const void* samples;
   const RecPlan* plans;
   const uint32_t* tile_first;   // n_rec + 1 prefix of main tiles
-  const float2* slow_pw;        // [nslow][wlen + 1]  p^k: weights of the tile-boundary state sums (global)
+  const float4* slow_pw4;       // [pairs][wpad]  {p_a^k, p_b^k}, zero for k > wlen: weights of the tile-boundary state sums (global)
+  int wpad;                     // entries per pole pair in slow_pw4 (>= wlen + 1 + 1024, so over-reads hit zeros)
   const float2* slow_tbl;       // [nslow][SLOW_TBL]  powers of m = lam^PM_CH used by the column scan (global)
   uint32_t* bits;
   int n_rec;
@@ -78,16 +79,22 @@ __device__ __forceinline__ float2 map22(float4 m, float fr, float fi, float2 acc
 
 // NT > 0: taps per polyphase row known at compile time (14 / 16 / 18: the window of NT + 7 columns lives in registers
 // and every tap index is an immediate offset into the parameter bank); NT == 0: runtime nt (rows padded to ntp % 4 == 0).
-template <typename TIn, int NT>
+// staged column c lives at X[j][pm_swz(c)]: bit 2 is flipped in odd 32-column blocks, so the 32-byte-strided LDS.128
+// window loads of a quarter warp (8 symbols per thread) hit 8 distinct 16-byte bank groups instead of 4
+__device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2); }
+
+// SPS > 0: samples per symbol known at compile time (even; float32 input): the staging loop is fully unrolled with all
+// of a thread's loads in flight before the first store; SPS == 0: runtime sps.
+template <typename TIn, int NT, int SPS>
 __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ float2 s_bnd[2][4][2];      // boundary-state partial sums [dir][slice][pole of the pair]
+  __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
   __shared__ float2 s_tot[8][4];         // warp totals of the column scan [warp][seq]
   __shared__ float2 s_car[8][4];         // state entering each warp [warp][seq]
   __shared__ float2 s_y0[9];             // y of each warp's first symbol (differential across warp edges)
   __shared__ double finit_sh[2 * FB_MAX_SLOW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
-  const int sps = a.sps;
+  const int sps = SPS ? SPS : a.sps;
   constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
   // ---- which recording / tile: largest r with tile_first[r] <= tile (32-way splitter search) -------------
   const uint32_t tile = blockIdx.x;
@@ -116,29 +123,60 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
   // A warp reads 32*sps consecutive samples; each 128-byte line is fetched from L2 once and re-hit in L1.
   {
     const int64_t n_a = (int64_t)a.n0 + (int64_t)ca * sps;          // sample index of staged element 0
-    const int ncols = min(P, cc + ns + a.dl + 4);
-    for (int c = tid; c < ncols; c += nthr) {
-      const int64_t n = n_a + (int64_t)c * sps;
-      float* dst = X + c;
-      if (n >= 0 && n + sps <= N) {
-        const uint64_t g = pl.off + (uint64_t)n;
-        if (sizeof(TIn) == 4 && (sps & 1) == 0 && (g & 1) == 0) {  // 8-byte aligned pairs
-          const float2* src = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.samples) + g);
-          const int P2 = 2 * P;
-          float* d2 = dst;
-#pragma unroll 5
-          for (int j = 0; j < sps; j += 2) {
-            const float2 v = __ldg(src + (j >> 1));
-            d2[0] = v.x;
-            d2[P] = v.y;
-            d2 += P2;
+    const int ncols = min(P, cc + ns + a.dl + 1);
+    bool done = false;
+    if constexpr (SPS > 0 && sizeof(TIn) == 4 && (SPS & 1) == 0) {
+      // 8-byte loads need an even element index: start one sample early when the column start is odd (the parity is
+      // the same for every column).  Loaded element k of column c is X[k - s][c]; k - s == -1 is X[sps-1][c-1].
+      const int s = (int)((pl.off + (uint64_t)n_a) & 1);
+      if (n_a - s >= 0 && n_a + (int64_t)(ncols + 1) * SPS <= N) {      // whole staged range inside the recording
+        const float* base = reinterpret_cast<const float*>(a.samples) + pl.off + n_a - s;
+        constexpr int KC = 4;
+        for (int c0 = tid; c0 < ncols + s; c0 += KC * nthr) {
+          constexpr int HS = SPS > 1 ? SPS / 2 : 1;
+          float2 v[KC][HS];
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int c = c0 + k * nthr;
+            if (c < ncols + s) {
+              const float2* src = reinterpret_cast<const float2*>(base + (int64_t)c * SPS);
+#pragma unroll
+              for (int i = 0; i < SPS / 2; ++i) v[k][i] = __ldg(src + i);
+            }
           }
-        } else {
-          for (int j = 0; j < sps; ++j) dst[j * P] = load_sample<TIn>(a.samples, g + j);
+#pragma unroll
+          for (int k = 0; k < KC; ++k) {
+            const int c = c0 + k * nthr;
+            if (c < ncols + s) {
+              float* dc = X + pm_swz(c);
+              if (s) {
+                if (c > 0) X[(SPS - 1) * P + pm_swz(c - 1)] = v[k][0].x;
+                if (c < ncols) {
+                  dc[0] = v[k][0].y;
+#pragma unroll
+                  for (int i = 1; i < SPS / 2; ++i) { dc[(2 * i - 1) * P] = v[k][i].x; dc[2 * i * P] = v[k][i].y; }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < SPS / 2; ++i) { dc[2 * i * P] = v[k][i].x; dc[(2 * i + 1) * P] = v[k][i].y; }
+              }
+            }
+          }
         }
-      } else {
-        for (int j = 0; j < sps; ++j)
-          dst[j * P] = (n + j >= 0 && n + j < N) ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
+        done = true;
+      }
+    }
+    if (!done) {
+      for (int c = tid; c < ncols; c += nthr) {
+        const int64_t n = n_a + (int64_t)c * sps;
+        float* dst = X + pm_swz(c);
+        if (n >= 0 && n + sps <= N) {
+          const uint64_t g = pl.off + (uint64_t)n;
+          for (int j = 0; j < sps; ++j) dst[j * P] = load_sample<TIn>(a.samples, g + j);
+        } else {
+          for (int j = 0; j < sps; ++j)
+            dst[j * P] = (n + j >= 0 && n + j < N) ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
+        }
       }
     }
   }
@@ -163,6 +201,46 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
     finit_sh[2 * tid + 1] = pr * si + pi * sr;
   }
 
+  // ---- tile-boundary states of the slow recursions (all pole pairs): Fst[d0] and Bfull[d1+1] as direct sums over the
+  // previous / next `wlen` samples against the power table {p_a^k, p_b^k} (zero beyond wlen).  2 directions x 4 slices
+  // of 128 samples per step, one warp per (direction, slice) job.
+  for (int pair = 0; pair < a.nslow; pair += 2) {
+    const float4* pw = a.slow_pw4 + (size_t)(pair >> 1) * a.wpad;
+    for (int job = warp; job < 8; job += nwarp) {
+      const bool fwd = job < 4;
+      const int slice = job & 3;
+      // forward: sample n_d0 - k has weight p^k, k = 1 .. cntf;  backward: sample n_e1 + k has weight p^k, k = 0 .. cntb-1
+      const int cntf = (int)min((int64_t)a.wlen, n_d0 - (near_left ? (int64_t)a.n0 : (int64_t)0));
+      const int cntb = (int)max((int64_t)0, min((int64_t)a.wlen + 1, N - n_e1));
+      const int klo = fwd ? 1 : 0, khi = fwd ? cntf : cntb - 1;
+      float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
+      for (int k0 = klo + 4 * (slice * 32 + lane); k0 <= khi; k0 += 512) {
+        float xv[4];
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = min(k0 + u, khi);                         // clamped address; the duplicate is zeroed below
+          const int64_t n = fwd ? n_d0 - k : n_e1 + k;
+          xv[u] = load_sample<TIn>(a.samples, pl.off + (uint64_t)n);
+          w[u] = __ldg(&pw[k0 + u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float x = (k0 + u <= khi) ? xv[u] : 0.f;
+          bs0 = bfma(x, make_float2(w[u].x, w[u].y), bs0);
+          bs1 = bfma(x, make_float2(w[u].z, w[u].w), bs1);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        bs0.x += __shfl_xor_sync(0xffffffffu, bs0.x, off); bs0.y += __shfl_xor_sync(0xffffffffu, bs0.y, off);
+        bs1.x += __shfl_xor_sync(0xffffffffu, bs1.x, off); bs1.y += __shfl_xor_sync(0xffffffffu, bs1.y, off);
+      }
+      if (lane == 0) { s_bnd[pair >> 1][fwd ? 0 : 1][slice][0] = bs0; s_bnd[pair >> 1][fwd ? 0 : 1][slice][1] = bs1; }
+    }
+  }
+  __syncthreads();                                  // staged samples, finit and the boundary sums are visible
+
   // this thread's PM_CH symbols e0 .. e0+7 (global d0 + e); y accumulates the slow part, then the FIR
   const int e0 = tid * PM_CH;
   const bool active = e0 < ns;
@@ -183,68 +261,25 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
     const bool two = pair + 1 < a.nslow;
     const int i1 = two ? pair + 1 : pair;
     const float2 lam0 = a.lam[pair], lam1 = a.lam[i1];
-    // (1) boundary sums: 2 directions x 4 slices of 128 samples per step, one warp per (direction, slice) job
-    for (int job = warp; job < 8; job += nwarp) {
-      const bool fwd = job < 4;
-      const int slice = job & 3;
-      const float2* pw0 = a.slow_pw + (size_t)pair * (a.wlen + 1);
-      const float2* pw1 = a.slow_pw + (size_t)i1 * (a.wlen + 1);
-      int cnt; int64_t nbeg; int kbeg, kstep;                 // sample n = nbeg + m has weight p^(kbeg + kstep*m)
-      if (fwd) {
-        const int64_t flo = near_left ? (int64_t)a.n0 : n_d0 - a.wlen;       // n in [flo, n_d0), weight p^(n_d0 - n)
-        cnt = (int)(n_d0 - flo); nbeg = flo; kbeg = cnt; kstep = -1;
-      } else {
-        cnt = (int)max((int64_t)0, min((int64_t)a.wlen, N - n_e1));           // n in [n_e1, n_e1 + cnt), weight p^(n - n_e1)
-        nbeg = n_e1; kbeg = 0; kstep = 1;
-      }
-      float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
-      for (int m0 = 4 * (slice * 32 + lane); m0 < cnt; m0 += 512) {
-        float xv[4];
-        float2 w0[4], w1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = m0 + u < cnt;
-          const int k = kbeg + kstep * (m0 + u);
-          xv[u] = ok ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(nbeg + m0 + u)) : 0.f;
-          w0[u] = ok ? __ldg(&pw0[k]) : make_float2(0.f, 0.f);
-          w1[u] = ok ? __ldg(&pw1[k]) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { bs0 = bfma(xv[u], w0[u], bs0); bs1 = bfma(xv[u], w1[u], bs1); }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        bs0.x += __shfl_xor_sync(0xffffffffu, bs0.x, off); bs0.y += __shfl_xor_sync(0xffffffffu, bs0.y, off);
-        bs1.x += __shfl_xor_sync(0xffffffffu, bs1.x, off); bs1.y += __shfl_xor_sync(0xffffffffu, bs1.y, off);
-      }
-      if (lane == 0) { s_bnd[fwd ? 0 : 1][slice][0] = bs0; s_bnd[fwd ? 0 : 1][slice][1] = bs1; }
-    }
-    __syncthreads();                                  // staged samples, finit and the boundary sums are visible
     // (2) per-column features of this thread's columns: z[0],z[1] forward (pole 0,1), z[2],z[3] backward
     float2 z[4][PM_CH];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int i = 0; i < PM_CH; ++i) z[k][i] = make_float2(0.f, 0.f);
-    float x0c[PM_CH];                                 // x[n_c] of the thread's columns (row 0)
-#pragma unroll
-    for (int i = 0; i < PM_CH; ++i) x0c[i] = 0.f;
     if (active) {
-      const float* rf = X + cc + e0;
+      const float* rf = X;
+      const int fo0 = pm_swz(cc + e0), fo1 = pm_swz(cc + e0 + 4);
       const float2* w0p = a.tab + a.wc_off + (size_t)pair * sps * 2;
       const float2* w1p = a.tab + a.wc_off + (size_t)i1 * sps * 2;
       for (int j = 0; j < sps; ++j) {
         float xs[PM_CH];
         if (NT) {
-          const float4 u0 = *reinterpret_cast<const float4*>(rf), u1 = *reinterpret_cast<const float4*>(rf + 4);
+          const float4 u0 = *reinterpret_cast<const float4*>(rf + fo0), u1 = *reinterpret_cast<const float4*>(rf + fo1);
           xs[0] = u0.x; xs[1] = u0.y; xs[2] = u0.z; xs[3] = u0.w; xs[4] = u1.x; xs[5] = u1.y; xs[6] = u1.z; xs[7] = u1.w;
         } else {
 #pragma unroll
-          for (int i = 0; i < PM_CH; ++i) xs[i] = rf[i];
-        }
-        if (j == 0) {
-#pragma unroll
-          for (int i = 0; i < PM_CH; ++i) x0c[i] = xs[i];
+          for (int i = 0; i < PM_CH; ++i) xs[i] = rf[pm_swz(cc + e0 + i)];
         }
         const float2 wf0 = w0p[2 * j], wb0 = w0p[2 * j + 1], wf1 = w1p[2 * j], wb1 = w1p[2 * j + 1];
 #pragma unroll
@@ -258,10 +293,10 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
       }
       // columns past the tile contribute nothing; the backward boundary state enters at the last column:
       // Bfull[ns-1] = zb[ns-1] + lam Bfull[ns]
-      const float2 bb0 = make_float2(s_bnd[1][0][0].x + s_bnd[1][1][0].x + s_bnd[1][2][0].x + s_bnd[1][3][0].x,
-                                     s_bnd[1][0][0].y + s_bnd[1][1][0].y + s_bnd[1][2][0].y + s_bnd[1][3][0].y);
-      const float2 bb1 = make_float2(s_bnd[1][0][1].x + s_bnd[1][1][1].x + s_bnd[1][2][1].x + s_bnd[1][3][1].x,
-                                     s_bnd[1][0][1].y + s_bnd[1][1][1].y + s_bnd[1][2][1].y + s_bnd[1][3][1].y);
+      const float2 bb0 = make_float2(s_bnd[pair >> 1][1][0][0].x + s_bnd[pair >> 1][1][1][0].x + s_bnd[pair >> 1][1][2][0].x + s_bnd[pair >> 1][1][3][0].x,
+                                     s_bnd[pair >> 1][1][0][0].y + s_bnd[pair >> 1][1][1][0].y + s_bnd[pair >> 1][1][2][0].y + s_bnd[pair >> 1][1][3][0].y);
+      const float2 bb1 = make_float2(s_bnd[pair >> 1][1][0][1].x + s_bnd[pair >> 1][1][1][1].x + s_bnd[pair >> 1][1][2][1].x + s_bnd[pair >> 1][1][3][1].x,
+                                     s_bnd[pair >> 1][1][0][1].y + s_bnd[pair >> 1][1][1][1].y + s_bnd[pair >> 1][1][2][1].y + s_bnd[pair >> 1][1][3][1].y);
       const float2 inj0 = cfma2(lam0, bb0, make_float2(0.f, 0.f)), inj1 = cfma2(lam1, bb1, make_float2(0.f, 0.f));
 #pragma unroll
       for (int i = 0; i < PM_CH; ++i) {
@@ -313,11 +348,13 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
       const float2* tb = (k & 1) ? tb1 : tb0;
       const float2 M = __ldg(&tb[38]);                // m^32
       if (k < 2) {                                    // state entering warp w from the left; warp 0: Fst[d0]
-        float2 c = make_float2(s_bnd[0][0][k].x + s_bnd[0][1][k].x + s_bnd[0][2][k].x + s_bnd[0][3][k].x,
-                               s_bnd[0][0][k].y + s_bnd[0][1][k].y + s_bnd[0][2][k].y + s_bnd[0][3][k].y);
+        float2 c = make_float2(s_bnd[pair >> 1][0][0][k].x + s_bnd[pair >> 1][0][1][k].x + s_bnd[pair >> 1][0][2][k].x + s_bnd[pair >> 1][0][3][k].x,
+                               s_bnd[pair >> 1][0][0][k].y + s_bnd[pair >> 1][0][1][k].y + s_bnd[pair >> 1][0][2][k].y + s_bnd[pair >> 1][0][3][k].y);
         if (near_left) {                              // + p^(n_d0 - n0) Fst[0]
           const int i = (k == 0) ? pair : i1;
-          const float2 pw = __ldg(&a.slow_pw[(size_t)i * (a.wlen + 1) + (int)(n_d0 - a.n0)]);
+          const float4 pw4 = __ldg(&a.slow_pw4[(size_t)(pair >> 1) * a.wpad + (int)(n_d0 - a.n0)]);
+          const float2 pw = (k == 0) ? make_float2(pw4.x, pw4.y) : make_float2(pw4.z, pw4.w);
+          (void)i;
           c = cfma2(pw, make_float2((float)finit_sh[2 * i], (float)finit_sh[2 * i + 1]), c);
         }
         for (int w = 0; w < nwarp; ++w) { s_car[w][k] = c; c = cfma2(M, c, s_tot[w][k]); }
@@ -349,6 +386,9 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
         sc[0] = cfma2(lam0, sc[0], z[0][i]);
         sc[1] = cfma2(lam1, sc[1], z[1][i]);
       }
+      float x0c[PM_CH];                               // x[n_c] of the thread's columns (row 0)
+#pragma unroll
+      for (int i = 0; i < PM_CH; ++i) x0c[i] = active ? X[pm_swz(cc + e0 + i)] : 0.f;
 #pragma unroll
       for (int i = PM_CH - 1; i >= 0; --i) {          // backward: Bfull[col] includes the column; Bst = Bfull - x[n_col]
         sc[2] = cfma2(lam0, sc[2], z[2][i]);
@@ -357,22 +397,24 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
         y[i] = map22(ab1, sc[3].x - x0c[i], sc[3].y, y[i]);
       }
     }
-    if (pair + 2 < a.nslow) __syncthreads();          // s_bnd / s_tot / s_car are rewritten by the next pair
+    if (pair + 2 < a.nslow) __syncthreads();          // s_tot / s_car are rewritten by the next pair
   }
-  if (a.nslow == 0) __syncthreads();
 
   // ---- fast part: register-tiled polyphase FIR at symbol instants --------------------------------
   //   y[s] += tapsR[j][t'] * X[j][e0 + PADL + s + t']   -- one FFMA2 per (complex tap, real sample), taps as uniform operands
   if (active) {
-    const float* row = X + e0;
+    const float* row = X;
     if (NT) {
       constexpr int NW = (PADL + NT + PM_CH - 1 + 3) / 4;      // float4 loads covering the window
       const float2* tp = a.tab;
+      int wo[NW];
+#pragma unroll
+      for (int q = 0; q < NW; ++q) wo[q] = pm_swz(e0 + 4 * q);
       for (int j = 0; j < sps; ++j) {
         float win[4 * NW];
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
-          const float4 u = reinterpret_cast<const float4*>(row)[q];
+          const float4 u = *reinterpret_cast<const float4*>(row + wo[q]);
           win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
         }
 #pragma unroll
@@ -389,11 +431,11 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
       for (int j = 0; j < sps; ++j) {
         float win[PM_CH + 4];
         {
-          const float4 u0 = reinterpret_cast<const float4*>(row)[0], u1 = reinterpret_cast<const float4*>(row)[1];
+          const float4 u0 = *reinterpret_cast<const float4*>(row + pm_swz(e0)), u1 = *reinterpret_cast<const float4*>(row + pm_swz(e0 + 4));
           win[0] = u0.x; win[1] = u0.y; win[2] = u0.z; win[3] = u0.w; win[4] = u1.x; win[5] = u1.y; win[6] = u1.z; win[7] = u1.w;
         }
         for (int t4 = 0; t4 < a.ntp; t4 += 4) {
-          const float4 u = reinterpret_cast<const float4*>(row)[2 + (t4 >> 2)];
+          const float4 u = *reinterpret_cast<const float4*>(row + pm_swz(e0 + 8 + t4));
           win[8] = u.x; win[9] = u.y; win[10] = u.z; win[11] = u.w;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -680,16 +722,18 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
   }
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
-    switch (ma.nt == ma.ntp ? ma.nt : 0) {
-#define FB_LAUNCH_MAIN(NTV)                                                                                               \
-      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      psk_main_kernel<TIn, NTV><<<n_tiles, nthreads, smem, h->stream>>>(ma)
-      case 14: FB_LAUNCH_MAIN(14); break;
-      case 16: FB_LAUNCH_MAIN(16); break;
-      case 18: FB_LAUNCH_MAIN(18); break;
-      default: FB_LAUNCH_MAIN(0); break;
+    const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
+#define FB_LAUNCH_MAIN(NTV, SPSV)                                                                                               \
+    do {                                                                                                                          \
+      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      psk_main_kernel<TIn, NTV, SPSV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
+    } while (0)
+    if (ntv == 16 && ma.sps == 10 && sizeof(TIn) == 4) FB_LAUNCH_MAIN(16, 10);      // 9600 sym/s at 96 kHz, float32 samples
+    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0);
+    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0);
+    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0);
+    else FB_LAUNCH_MAIN(0, 0);
 #undef FB_LAUNCH_MAIN
-    }
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
   }
@@ -820,8 +864,9 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     for (int j = 0; j < d.sps; ++j)
       for (int t = 0; t < d.nt; ++t)
         ma.tab[j * ntp + t] = make_float2(taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2], taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2 + 1]);
-    const int ns_ = std::max(1, d.nslow);
-    std::vector<float> pwv((size_t)ns_ * (wlen + 1) * 2, 0.f), tbl((size_t)ns_ * SLOW_TBL * 2, 0.f);
+    const int npairs = std::max(1, (d.nslow + 1) / 2), ns_ = std::max(1, d.nslow);
+    const int wpad = (wlen + 1 + 1024 + 3) / 4 * 4;
+    std::vector<float> pwv((size_t)npairs * wpad * 4, 0.f), tbl((size_t)ns_ * SLOW_TBL * 2, 0.f);
     for (int i = 0; i < d.nslow; ++i) {
       const double pr = d.slow_p[2 * i], pi = d.slow_p[2 * i + 1];
       std::vector<double> pk((size_t)(std::max(wlen, d.sps) + 1) * 2);
@@ -831,8 +876,8 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
         pk[2 * k + 1] = pk[2 * k - 2] * pi + pk[2 * k - 1] * pr;
       }
       for (int k = 0; k <= wlen; ++k) {
-        pwv[((size_t)i * (wlen + 1) + k) * 2] = (float)pk[2 * k];
-        pwv[((size_t)i * (wlen + 1) + k) * 2 + 1] = (float)pk[2 * k + 1];
+        pwv[((size_t)(i >> 1) * wpad + k) * 4 + 2 * (i & 1)] = (float)pk[2 * k];
+        pwv[((size_t)(i >> 1) * wpad + k) * 4 + 2 * (i & 1) + 1] = (float)pk[2 * k + 1];
       }
       for (int j = 0; j < d.sps; ++j) {
         ma.tab[ma.wc_off + (i * d.sps + j) * 2] = make_float2((float)pk[2 * (d.sps - j)], (float)pk[2 * (d.sps - j) + 1]);
@@ -858,7 +903,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
     ma.samples = d_samples; ma.plans = (const RecPlan*)h->plans.p; ma.tile_first = (const uint32_t*)h->tile_first.p;
-    ma.slow_pw = (const float2*)tabs; ma.slow_tbl = (const float2*)(tabs + o_tb); ma.bits = (uint32_t*)h->bits.p;
+    ma.slow_pw4 = (const float4*)tabs; ma.wpad = wpad; ma.slow_tbl = (const float2*)(tabs + o_tb); ma.bits = (uint32_t*)h->bits.p;
     ma.n_rec = n_rec; ma.sps = d.sps; ma.n0 = d.n0; ma.bps = bps; ma.nt = d.nt; ma.ntp = ntp; ma.dl = d.dl; ma.dh = d.dh;
     ma.nslow = d.nslow; ma.wlen = wlen; ma.pad_bp = d.pad_bp; ma.T = T; ma.P = P; ma.padl = padl;
     ma.rho = make_float2(d.rho[0], d.rho[1]);
