@@ -63,6 +63,7 @@ extern "C" fb_handle* fb_create(int device) {
   }
   fb_handle* h = new fb_handle();
   h->device = device;
+  h->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -38,7 +38,7 @@ struct EdgeJob {
 };
 
 struct fb_handle {
-  int device = 0;
+  int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
   bool profiling = false, k_recorded = false;

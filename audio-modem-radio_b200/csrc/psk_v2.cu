@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #define PM_CH 8              // columns (= symbols) per thread: FIR register tile and slow-pole scan chunk
 #define PM_THREADS 256
@@ -771,8 +772,11 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     // the FIR windows are whole float4s: they over-read a few columns right of the last tap
     const int win = spec ? (padl + d.nt + PM_CH - 1 + 3) / 4 * 4 : PM_CH + ntp;
     if ((size_t)d.sps * ntp + 2 * (size_t)std::max(1, d.nslow) * d.sps > PM_MAXTAB) emulate_only = true;   // constant table full
-    const size_t budget = 100 * 1024;                              // two CTAs per SM
-    for (T = PM_THREADS * PM_CH - 32; T >= 32; T -= 32) {
+    size_t budget = 100 * 1024;                                    // two CTAs per SM
+    int tmax = PM_THREADS * PM_CH - 32;
+    if (const char* e = getenv("FB_PSK_T")) { tmax = std::max(32, std::min(tmax, atoi(e) / 32 * 32)); }   // tuning knob
+    if (const char* e = getenv("FB_PSK_SMEM_KB")) { budget = (size_t)std::max(8, atoi(e)) * 1024; }
+    for (T = tmax; T >= 32; T -= 32) {
       P = (T + 1 + PM_CH - 1) / PM_CH * PM_CH + win;
       smem = (size_t)d.sps * P * 4;
       if (smem <= budget) break;

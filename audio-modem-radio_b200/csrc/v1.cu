@@ -15,16 +15,22 @@
 #include <algorithm>
 
 enum { V1_BPSK = 0, V1_QPSK = 1, V1_PSK8 = 2, V1_OFDM = 3, V1_FSK = 4 };
-#define V1_TILE 256
+#define V1_THREADS 256
 
 struct V1Args {
-  const void* samples;           // prefiltered float32 buffer for FSK, caller samples otherwise
+  const void* samples;           // prefiltered float32 buffer for FSK, caller samples otherwise (16-byte aligned)
   const RecPlan* plans;          // nsym = symbols, word_off = bit-stream words (FSK+UART) , out_off/out_cap
   const uint32_t* tile_first;
-  const double2* table;          // [nf][len] complex weights (float64)
+  const double2* table;          // [nfu][len] complex weights (float64), unique rows only
   uint8_t* out;
   uint32_t* bits;                // workspace words (uart mode) or nullptr
-  int n_rec, mode, sps, off0, len, nf, bpsym, to_workspace;
+  uint64_t total_bytes;          // bytes of the samples buffer: bulk copies never read past its last whole 16 bytes
+  int n_rec, mode, sps, off0, len, nf, nfu, bpsym, to_workspace;
+  int G;                         // lanes per symbol (largest power of two dividing sps, <= 32): conflict-free strided LDS
+  int S;                         // symbols per tile
+  int raw_bytes;                 // shared-memory bytes reserved for one staged tile (multiple of 128)
+  uint32_t n_tiles;
+  int map[8];                    // bin m -> unique row (bits 0-7), conjugate flag (bit 8)
 };
 
 __device__ __forceinline__ uint32_t quadrant_code(double re, double im) {      // B.5
@@ -34,114 +40,209 @@ __device__ __forceinline__ uint32_t quadrant_code(double re, double im) {      /
   return 2u;
 }
 
-template <typename TIn>
-__global__ void __launch_bounds__(V1_TILE) v1_corr_kernel(const V1Args a) {
-  extern __shared__ __align__(16) unsigned char v1_smem[];
-  double2* W = reinterpret_cast<double2*>(v1_smem);                       // [nf][len]
-  uint32_t* codes = reinterpret_cast<uint32_t*>(W + (size_t)a.nf * a.len);   // [V1_TILE]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int lo = 0, hi = a.n_rec;
-  const uint32_t tile = blockIdx.x;
-  while (hi - lo > 1) {
-    const int step = (hi - lo + 31) >> 5;
-    const int probe = lo + (lane + 1) * step;
-    const bool le = probe < hi && __ldg(&a.tile_first[probe]) <= tile;
-    const int cnt = __popc(__ballot_sync(0xffffffffu, le));
-    const int nlo = lo + cnt * step;
-    hi = min(hi, nlo + step);
-    lo = nlo;
+// B.6: phi = atan2(Q, I) mod 2 pi; code = #{t in 1,3,..,13 : phi >= t pi/8}.  Evaluated with cross products against the
+// seven sector edges (exact up to the rounding of one product); symbols within 1e-12 of an edge take the atan2 path.
+__device__ __forceinline__ uint32_t psk8_code(double I, double Q) {
+  const double c1 = 0.92387953251128674, s1 = 0.38268343236508977;           // cos, sin of pi/8
+  const double ec[7] = {c1, s1, -s1, -c1, -c1, -s1, s1}, es[7] = {s1, c1, c1, s1, -s1, -c1, -c1};   // t = 1,3,..,13
+  const double tol = 1e-12 * (fabs(I) + fabs(Q));
+  uint32_t code = 0;
+  bool near = false;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const double cr = ec[t] * Q - es[t] * I;                                  // |v| sin(phi - theta_t)
+    near |= fabs(cr) <= tol;
+    const bool ge = (t < 4) ? (Q < 0.0 || cr >= 0.0) : (Q < 0.0 && cr >= 0.0);
+    code += ge ? 1u : 0u;
   }
-  const RecPlan pl = a.plans[lo];
-  const int k0 = (int)(tile - a.tile_first[lo]) * V1_TILE;                 // first symbol of the tile
-  const int ns = min(V1_TILE, pl.nsym - k0);
-  for (int i = tid; i < a.nf * a.len; i += V1_TILE) W[i] = a.table[i];
-  codes[tid] = 0;
+  if (near) {
+    double phi = atan2(Q, I);
+    if (phi < 0.0) phi += 2.0 * 3.141592653589793;
+    code = 0;
+#pragma unroll
+    for (int t = 1; t <= 13; t += 2) code += (phi >= t * (3.141592653589793 / 8.0)) ? 1u : 0u;
+  }
+  return code;
+}
+
+template <typename T> __device__ __forceinline__ double smem_sample_d(const unsigned char* p, int i);
+template <> __device__ __forceinline__ double smem_sample_d<float>(const unsigned char* p, int i) { return (double)reinterpret_cast<const float*>(p)[i]; }
+template <> __device__ __forceinline__ double smem_sample_d<double>(const unsigned char* p, int i) { return reinterpret_cast<const double*>(p)[i]; }
+template <> __device__ __forceinline__ double smem_sample_d<int16_t>(const unsigned char* p, int i) {
+  return (double)reinterpret_cast<const int16_t*>(p)[i] * (1.0 / 32768.0);
+}
+
+// Persistent CTAs, one producer thread + 256 consumer threads.  CTA b owns the contiguous tile range
+// [b*q, (b+1)*q); a tile is S symbols of one recording, contiguous in HBM.  The producer walks its range (recording,
+// first symbol) incrementally and brings each tile into a V1_STAGES-deep shared-memory ring with ONE bulk asynchronous
+// copy (cp.async.bulk -> UBLKCP, completion on the stage's `full` mbarrier): no per-thread load instructions, full
+// 16-byte coalescing whatever sps is, and V1_STAGES tiles in flight per CTA so neither the tile lookup nor the DRAM
+// latency is ever exposed.  Consumers: G lanes share a symbol (G = largest power of two dividing sps, so the strided
+// shared-memory reads are bank-conflict free); correlations accumulate in float64 (App. B: freeze at float64
+// accumulation) and are reduced over the G lanes with shuffles; decisions are packed 32 bits per thread and stored.
+#define V1_STAGES 4
+struct V1Tile {                   // written by the producer, read by the consumers once `full` completes
+  uint64_t out_off, out_cap, word_off;
+  int32_t nsym, k0, ns, skew;
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar_s), "r"(parity) : "memory");
+  }
+}
+
+template <typename TIn, int NFU>
+__global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a) {
+  extern __shared__ __align__(128) unsigned char v1_smem[];
+  __shared__ __align__(8) unsigned long long full[V1_STAGES], empty[V1_STAGES];
+  __shared__ V1Tile desc[V1_STAGES];
+  unsigned char* raw = v1_smem;                                              // [V1_STAGES][raw_bytes]
+  double2* W = reinterpret_cast<double2*>(v1_smem + (size_t)V1_STAGES * a.raw_bytes);   // [NFU][len]
+  uint16_t* codes = reinterpret_cast<uint16_t*>(W + (size_t)NFU * a.len);    // [S]
+  const int tid = threadIdx.x;
+  const uint32_t q = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t_begin = min(a.n_tiles, blockIdx.x * q), t_end = min(a.n_tiles, t_begin + q);
+  const uint32_t full_s = (uint32_t)__cvta_generic_to_shared(full), empty_s = (uint32_t)__cvta_generic_to_shared(empty);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < V1_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_s + 8 * s));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < V1_THREADS)
+    for (int i = tid; i < NFU * a.len; i += V1_THREADS) W[i] = (i < a.nfu * a.len) ? __ldg(&a.table[i]) : make_double2(0.0, 0.0);
   __syncthreads();
 
-  auto decide = [&](const double* fr, const double* fi) -> uint32_t {
-    switch (a.mode) {
-      case V1_BPSK: return fr[0] > 0.0 ? 0u : 1u;                          // B.4: '0' if I > 0 else '1'
-      case V1_QPSK: return quadrant_code(fr[0], fi[0]);
-      case V1_PSK8: {                                                      // B.6
-        double phi = atan2(fi[0], fr[0]);
-        if (phi < 0.0) phi += 2.0 * 3.141592653589793;
-        uint32_t code = 0;
-#pragma unroll
-        for (int t = 1; t <= 13; t += 2) code += (phi >= t * (3.141592653589793 / 8.0)) ? 1u : 0u;
-        return code;
+  if (tid >= V1_THREADS) {
+    // ================================ producer (one thread) ================================
+    if (tid != V1_THREADS || t_begin >= t_end) return;
+    int lo = 0, hi = a.n_rec;                                                // largest r with tile_first[r] <= t_begin
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(&a.tile_first[mid]) <= t_begin) lo = mid; else hi = mid; }
+    int rec = lo;
+    RecPlan pl = a.plans[rec];
+    int k0 = (int)(t_begin - __ldg(&a.tile_first[rec])) * a.S;
+    for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
+      while (k0 >= pl.nsym) { pl = a.plans[++rec]; k0 = 0; }                 // next recording that has symbols
+      const int st = i % V1_STAGES;
+      if (i >= V1_STAGES) mbar_wait(empty_s + 8 * st, ((i / V1_STAGES) - 1) & 1);
+      const int ns = min(a.S, pl.nsym - k0);
+      // bytes [b0, b1) of the batch buffer, widened to 16-byte boundaries (never past the buffer's last whole 16 bytes)
+      const uint64_t b0 = (pl.off + (uint64_t)k0 * a.sps) * sizeof(TIn), b1 = b0 + (uint64_t)ns * a.sps * sizeof(TIn);
+      const uint64_t a0 = b0 & ~15ull;
+      uint64_t a1 = min((b1 + 15) & ~15ull, a.total_bytes & ~15ull);
+      if (a1 < a0) a1 = a0;
+      unsigned char* dst = raw + (size_t)st * a.raw_bytes;
+      for (uint64_t g = max(a1, b0); g < b1; ++g) dst[g - a0] = __ldg(reinterpret_cast<const unsigned char*>(a.samples) + g);
+      V1Tile d;
+      d.out_off = pl.out_off; d.out_cap = pl.out_cap; d.word_off = pl.word_off;
+      d.nsym = pl.nsym; d.k0 = k0; d.ns = ns; d.skew = (int)(b0 - a0);
+      desc[st] = d;
+      const uint32_t fb = full_s + 8 * st;
+      if (a1 > a0) {
+        const uint32_t nbytes = (uint32_t)(a1 - a0);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(nbytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<const unsigned char*>(a.samples) + a0),
+                       "r"(nbytes), "r"(fb) : "memory");
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
       }
-      case V1_OFDM: {                                                      // B.7: bins in order, 2 bits each
-        uint32_t code = 0;
-        for (int m = 0; m < a.nf; ++m) code = (code << 2) | quadrant_code(fr[m], fi[m]);
-        return code;
-      }
-      default: {                                                           // V1_FSK: bit = p_mark > p_space
-        const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[1] * fr[1] + fi[1] * fi[1];
-        return pm > ps ? 1u : 0u;
-      }
+      k0 += a.S;
     }
-  };
+    return;
+  }
 
-  constexpr int MAXF = 8;
-  if (a.sps <= 32) {
-    if (tid < ns) {                                                        // thread per symbol
-      const uint64_t base = pl.off + (uint64_t)(k0 + tid) * a.sps + a.off0;
-      double fr[MAXF], fi[MAXF];
+  // ================================ consumers (V1_THREADS threads) ================================
+  const int G = a.G, SP = V1_THREADS / G, grp = tid / G, l = tid - grp * G;
+  for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
+    const int st = i % V1_STAGES;
+    mbar_wait(full_s + 8 * st, (i / V1_STAGES) & 1);
+    const V1Tile d = desc[st];
+    const unsigned char* xs = raw + (size_t)st * a.raw_bytes + d.skew;
+    const int ns = d.ns;
+    for (int s0 = 0; s0 < ns; s0 += SP) {
+      const int s = s0 + grp;
+      const bool valid = s < ns;
+      double fr[NFU], fi[NFU];
 #pragma unroll
-      for (int m = 0; m < MAXF; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
-      for (int j = 0; j < a.len; ++j) {
-        const double x = load_sample_d<TIn>(a.samples, base + j);
+      for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
+      if (valid) {
+        const int base = s * a.sps + a.off0;
+#pragma unroll 2
+        for (int j = l; j < a.len; j += G) {
+          const double x = smem_sample_d<TIn>(xs, base + j);
 #pragma unroll
-        for (int m = 0; m < MAXF; ++m)
-          if (m < a.nf) { const double2 w = W[m * a.len + j]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+          for (int m = 0; m < NFU; ++m) { const double2 w = W[m * a.len + j]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+        }
       }
-      codes[tid] = decide(fr, fi);
-    }
-  } else {
-    for (int s = warp; s < ns; s += V1_TILE / 32) {                        // warp per symbol
-      const uint64_t base = pl.off + (uint64_t)(k0 + s) * a.sps + a.off0;
-      double fr[MAXF], fi[MAXF];
+      for (int off = G >> 1; off > 0; off >>= 1) {
 #pragma unroll
-      for (int m = 0; m < MAXF; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
-      for (int j = lane; j < a.len; j += 32) {
-        const double x = load_sample_d<TIn>(a.samples, base + j);
-#pragma unroll
-        for (int m = 0; m < MAXF; ++m)
-          if (m < a.nf) { const double2 w = W[m * a.len + j]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+        for (int m = 0; m < NFU; ++m) {
+          fr[m] += __shfl_xor_sync(0xffffffffu, fr[m], off);
+          fi[m] += __shfl_xor_sync(0xffffffffu, fi[m], off);
+        }
       }
+      if (valid && l == 0) {
+        uint32_t code;
+        switch (a.mode) {
+          case V1_BPSK: code = fr[0] > 0.0 ? 0u : 1u; break;                    // B.4: '0' if I > 0 else '1'
+          case V1_QPSK: code = quadrant_code(fr[0], fi[0]); break;
+          case V1_PSK8: code = psk8_code(fr[0], fi[0]); break;
+          case V1_OFDM: {                                                        // B.7: bins in order, 2 bits each
+            code = 0;
+            for (int m = 0; m < a.nf; ++m) {
+              const int r = a.map[m] & 0xff;
+              double re = 0.0, im = 0.0;
 #pragma unroll
-      for (int m = 0; m < MAXF; ++m)
-        if (m < a.nf) {
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            fr[m] += __shfl_xor_sync(0xffffffffu, fr[m], off);
-            fi[m] += __shfl_xor_sync(0xffffffffu, fi[m], off);
+              for (int u = 0; u < NFU; ++u) if (u == r) { re = fr[u]; im = fi[u]; }
+              if (a.map[m] & 0x100) im = -im;                                    // F[L - m] = conj(F[m]) for real input
+              code = (code << 2) | quadrant_code(re, im);
+            }
+            break;
+          }
+          default: {                                                             // V1_FSK: bit = p_mark > p_space
+            constexpr int I1 = NFU > 1 ? 1 : 0;
+            const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
+            code = pm > ps ? 1u : 0u;
           }
         }
-      if (lane == 0) codes[s] = decide(fr, fi);
+        codes[s] = (uint16_t)code;
+      }
     }
-  }
-  __syncthreads();
-  // ---- pack: V1_TILE * bpsym bits = 8 * bpsym whole words per tile ---------------------------------------
-  const int nwords = (ns * a.bpsym + 31) / 32;
-  for (int w = tid; w < nwords; w += V1_TILE) {
-    uint32_t word = 0;
-    for (int b = 0; b < 32; ++b) {
-      const int bit = w * 32 + b;
-      const int sym = bit / a.bpsym, pos = bit - sym * a.bpsym;
-      const uint32_t v = (sym < ns) ? ((codes[sym] >> (a.bpsym - 1 - pos)) & 1u) : 0u;
-      word = (word << 1) | v;
-    }
-    const uint64_t widx = (uint64_t)k0 * a.bpsym / 32 + w;
-    if (a.to_workspace) {
-      a.bits[pl.word_off + widx] = __byte_perm(word, 0, 0x0123);
-    } else {
-      const uint64_t nbytes = min((uint64_t)pl.nsym * a.bpsym / 8, pl.out_cap);   // truncate to a multiple of 8 bits
-      uint8_t* o = a.out + pl.out_off;
+    asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");               // codes complete; the stage's samples are consumed
+    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8 * st) : "memory");
+    // ---- pack: ns * bpsym bits, 32 per thread, big-endian words ------------------------------------------------
+    const int nwords = (ns * a.bpsym + 31) / 32;
+    for (int w = tid; w < nwords; w += V1_THREADS) {
+      uint32_t word = 0;
+      int sym = (w * 32) / a.bpsym, pos = (w * 32) - sym * a.bpsym;
+      uint32_t cur = sym < ns ? codes[sym] : 0u;
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b) {
+        word = (word << 1) | ((cur >> (a.bpsym - 1 - pos)) & 1u);
+        if (++pos == a.bpsym) { pos = 0; ++sym; cur = sym < ns ? codes[sym] : 0u; }
+      }
+      const uint64_t widx = (uint64_t)d.k0 * a.bpsym / 32 + w;
+      if (a.to_workspace) {
+        a.bits[d.word_off + widx] = __byte_perm(word, 0, 0x0123);
+      } else {
+        const uint64_t nbytes = min((uint64_t)d.nsym * a.bpsym / 8, d.out_cap);   // truncate to a multiple of 8 bits
+        uint8_t* o = a.out + d.out_off;
+        if (widx * 4 + 4 <= nbytes) {
+          *reinterpret_cast<uint32_t*>(o + widx * 4) = __byte_perm(word, 0, 0x0123);
+        } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (widx * 4 + k < nbytes) o[widx * 4 + k] = (uint8_t)(word >> (24 - 8 * k));
+          for (int k = 0; k < 4; ++k)
+            if (widx * 4 + k < nbytes) o[widx * 4 + k] = (uint8_t)(word >> (24 - 8 * k));
+        }
+      }
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");               // codes may be overwritten by the next tile
   }
 }
 
@@ -261,6 +362,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
                                  uint64_t* out_len, int32_t* status) {
   if (!h || !pp || !table || n_rec < 0 || !offsets || !out_offsets) return FB_EINVAL;
   if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
+  if ((flags & FB_SAMPLES_ON_DEVICE) && ((uintptr_t)samples & 15)) return FB_EINVAL;   // bulk copies need a 16-byte aligned batch buffer
   const fb_v1_params& p = *pp;
   if (p.sps < 1 || p.len < 1 || p.off0 < 0 || p.off0 + p.len > p.sps || p.nf < 1 || p.nf > 8 || p.bits_per_sym < 1 ||
       p.bits_per_sym > 16 || p.mode < V1_BPSK || p.mode > V1_FSK)
@@ -268,6 +370,38 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   FB_CUDA(h, cudaSetDevice(h->device));
   if (n_rec == 0) return FB_OK;
   const size_t esz = dtype == FB_F32 ? 4 : dtype == FB_F64 ? 8 : 2;
+  // ---- unique correlator rows: for a real input F[L-m] = conj(F[m]), so an OFDM bin whose row is the conjugate of an
+  // earlier row costs nothing (B.7's FFT has exactly that symmetry)
+  int map[8] = {0, 1, 2, 3, 4, 5, 6, 7}, nfu = p.nf;
+  std::vector<double> utab((size_t)p.nf * p.len * 2);
+  if (p.mode == V1_OFDM) {
+    nfu = 0;
+    for (int m = 0; m < p.nf; ++m) {
+      const double* row = table + (size_t)m * p.len * 2;
+      int hit = -1;
+      for (int u = 0; u < nfu && hit < 0; ++u) {
+        bool same = true;
+        for (int j = 0; j < p.len && same; ++j)
+          same = fabs(utab[((size_t)u * p.len + j) * 2] - row[2 * j]) <= 1e-12 && fabs(utab[((size_t)u * p.len + j) * 2 + 1] + row[2 * j + 1]) <= 1e-12;
+        if (same) hit = u;
+      }
+      if (hit >= 0) { map[m] = hit | 0x100; continue; }
+      std::copy(row, row + (size_t)p.len * 2, utab.begin() + (size_t)nfu * p.len * 2);
+      map[m] = nfu++;
+    }
+  } else {
+    std::copy(table, table + (size_t)p.nf * p.len * 2, utab.begin());
+  }
+  const int NFU = nfu <= 1 ? 1 : nfu <= 2 ? 2 : nfu <= 4 ? 4 : 8;
+  // ---- tile geometry: G lanes per symbol, S symbols (multiple of 32) per tile, ~12 KB of samples per tile
+  // (the pre-filtered FSK path always correlates float32)
+  const size_t kesz = p.prefilter ? 4 : esz;
+  int G = 1;
+  while (G < 32 && p.sps % (2 * G) == 0) G *= 2;
+  int S = (int)std::max<size_t>(32, std::min<size_t>(1024, (12288 / ((size_t)p.sps * kesz)) / 32 * 32));
+  const size_t raw_bytes = ((size_t)S * p.sps * kesz + 16 + 127) / 128 * 128;
+  const size_t smem = V1_STAGES * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
+  if (smem > 200 * 1024) return FB_EUNSUPPORTED;
   std::vector<RecPlan> plans(n_rec);
   std::vector<uint32_t> tile_first(n_rec + 1, 0);
   uint32_t n_tiles = 0;
@@ -282,7 +416,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
     if (p.prefilter && (int64_t)q.n <= p.bp_pad) { q.status = FB_ST_TOO_SHORT; q.nsym = q.ndsym = 0; tile_first[r] = n_tiles; continue; }
     q.nsym = q.ndsym = (int32_t)std::min<uint64_t>(q.n / (uint64_t)p.sps, 0x7fffffff);
     tile_first[r] = n_tiles;
-    n_tiles += (uint32_t)((q.nsym + V1_TILE - 1) / V1_TILE);
+    n_tiles += (uint32_t)((q.nsym + S - 1) / S);
     words += ((uint64_t)q.nsym * p.bits_per_sym + 31) / 32 + 2;
     maxN = std::max<int64_t>(maxN, (int64_t)q.n);
   }
@@ -308,7 +442,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   if (p.uart && (rc = fb_ensure(h, h->bits, (size_t)(words + 4) * 4))) return rc;
   FB_CUDA(h, cudaMemcpyAsync(h->plans.p, plans.data(), (size_t)n_rec * sizeof(RecPlan), cudaMemcpyHostToDevice, h->stream));
   FB_CUDA(h, cudaMemcpyAsync(h->tile_first.p, tile_first.data(), (size_t)(n_rec + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-  FB_CUDA(h, cudaMemcpyAsync(h->taps.p, table, (size_t)p.nf * p.len * 16, cudaMemcpyHostToDevice, h->stream));
+  FB_CUDA(h, cudaMemcpyAsync(h->taps.p, utab.data(), (size_t)nfu * p.len * 16, cudaMemcpyHostToDevice, h->stream));
 
   int kdtype = dtype;
   if (p.prefilter) {
@@ -339,20 +473,29 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   a.table = (const double2*)h->taps.p; a.out = d_out; a.bits = p.uart ? (uint32_t*)h->bits.p : nullptr;
   a.n_rec = n_rec; a.mode = p.mode; a.sps = p.sps; a.off0 = p.off0; a.len = p.len; a.nf = p.nf; a.bpsym = p.bits_per_sym;
   a.to_workspace = p.uart ? 1 : 0;
-  const size_t smem = (size_t)p.nf * p.len * 16 + V1_TILE * 4;
-  if (smem > 200 * 1024) return FB_EUNSUPPORTED;
+  a.nfu = nfu; a.G = G; a.S = S; a.raw_bytes = (int)raw_bytes;
+  a.total_bytes = (uint64_t)total_samples * kesz; a.n_tiles = n_tiles;
+  for (int m = 0; m < 8; ++m) a.map[m] = map[m];
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
-    if (kdtype == FB_F32) {
-      FB_CUDA(h, cudaFuncSetAttribute(v1_corr_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      v1_corr_kernel<float><<<n_tiles, V1_TILE, smem, h->stream>>>(a);
-    } else if (kdtype == FB_F64) {
-      FB_CUDA(h, cudaFuncSetAttribute(v1_corr_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      v1_corr_kernel<double><<<n_tiles, V1_TILE, smem, h->stream>>>(a);
-    } else {
-      FB_CUDA(h, cudaFuncSetAttribute(v1_corr_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      v1_corr_kernel<int16_t><<<n_tiles, V1_TILE, smem, h->stream>>>(a);
-    }
+#define FB_V1_LAUNCH(T, N)                                                                                            \
+    do {                                                                                                                \
+      FB_CUDA(h, cudaFuncSetAttribute(v1_corr_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      int per_sm = 1;                                                                                                   \
+      FB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v1_corr_kernel<T, N>, V1_THREADS + 32, smem)); \
+      const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, per_sm) * (uint32_t)h->sm_count);         \
+      v1_corr_kernel<T, N><<<grid, V1_THREADS + 32, smem, h->stream>>>(a);                                              \
+    } while (0)
+#define FB_V1_DISPATCH(T)                                                                         \
+    do {                                                                                           \
+      if (NFU == 1) FB_V1_LAUNCH(T, 1); else if (NFU == 2) FB_V1_LAUNCH(T, 2);                     \
+      else if (NFU == 4) FB_V1_LAUNCH(T, 4); else FB_V1_LAUNCH(T, 8);                              \
+    } while (0)
+    if (kdtype == FB_F32) FB_V1_DISPATCH(float);
+    else if (kdtype == FB_F64) FB_V1_DISPATCH(double);
+    else FB_V1_DISPATCH(int16_t);
+#undef FB_V1_DISPATCH
+#undef FB_V1_LAUNCH
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
   }

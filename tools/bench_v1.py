@@ -14,6 +14,7 @@ ap.add_argument("--recordings", type=int, default=256)
 ap.add_argument("--seconds", type=int, default=180)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--dtype", default="f32")
+ap.add_argument("--only", default="")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 eng = fbdsp.Engine(0)
@@ -31,6 +32,8 @@ esz = batch.element_size()
 for name, (p, table) in {"v1_qpsk_9600": g.psk_params(g.V1_QPSK, 9600, 9600.0), "v1_bpsk_9600": g.psk_params(g.V1_BPSK, 9600, 3000.0),
                          "v1_psk8_38400": g.psk_params(g.V1_PSK8, 38400, 12000.0), "v1_qpsk_1200": g.psk_params(g.V1_QPSK, 1200, 3000.0),
                          "v1_ofdm8_9600": g.ofdm_params(9600, 8), "v1_ofdm4_4800": g.ofdm_params(4800, 4)}.items():
+    if args.only and name not in args.only.split(','):
+        continue
     size = (int(eng.lib.fb_v1_out_bound(ctypes.byref(p), n)) + 7) // 4 * 4
     out_offsets = np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(size)
     out = torch.empty(n_rec * size + 16, dtype=torch.uint8, device=dev)
