@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 enum { V1_BPSK = 0, V1_QPSK = 1, V1_PSK8 = 2, V1_OFDM = 3, V1_FSK = 4 };
 #define V1_THREADS 256
@@ -30,6 +31,7 @@ struct V1Args {
   int S;                         // symbols per tile
   int raw_bytes;                 // shared-memory bytes reserved for one staged tile (multiple of 128)
   uint32_t n_tiles;
+  int stages;
   int map[8];                    // bin m -> unique row (bits 0-7), conjugate flag (bit 8)
 };
 
@@ -80,17 +82,43 @@ template <> __device__ __forceinline__ double smem_sample_d<int16_t>(const unsig
 // latency is ever exposed.  Consumers: G lanes share a symbol (G = largest power of two dividing sps, so the strided
 // shared-memory reads are bank-conflict free); correlations accumulate in float64 (App. B: freeze at float64
 // accumulation) and are reduced over the G lanes with shuffles; decisions are packed 32 bits per thread and stored.
-#define V1_STAGES 4
+#define V1_STAGES 8           // ring capacity; a.stages (<= V1_STAGES) are used
 struct V1Tile {                   // written by the producer, read by the consumers once `full` completes
   uint64_t out_off, out_cap, word_off;
   int32_t nsym, k0, ns, skew;
 };
 
+// word `widx` of the recording's decided bit stream (MSB-first): to the bit workspace (UART mode) or straight into the
+// caller's slot, truncated to whole bytes of the stream and to the slot capacity
+__device__ __forceinline__ void v1_store_word(const V1Args& a, const V1Tile& d, uint64_t widx, uint32_t word) {
+  if (a.to_workspace) {
+    a.bits[d.word_off + widx] = __byte_perm(word, 0, 0x0123);
+  } else {
+    const uint64_t nbytes = min((uint64_t)d.nsym * a.bpsym / 8, d.out_cap);
+    uint8_t* o = a.out + d.out_off;
+    if (widx * 4 + 4 <= nbytes) {
+      *reinterpret_cast<uint32_t*>(o + widx * 4) = __byte_perm(word, 0, 0x0123);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (widx * 4 + k < nbytes) o[widx * 4 + k] = (uint8_t)(word >> (24 - 8 * k));
+    }
+  }
+}
+
+// BACKOFF: the producer is several tiles ahead -- let the hardware suspend it on the barrier (try_wait's suspend-time
+// hint) instead of burning issue slots in a spin loop
+template <bool BACKOFF>
 __device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
   uint32_t done = 0;
-  while (!done) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(bar_s), "r"(parity) : "memory");
+  while (true) {
+    if (BACKOFF)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar_s), "r"(parity), "r"(20000u) : "memory");
+    else
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(done) : "r"(bar_s), "r"(parity) : "memory");
+    if (done) break;
   }
 }
 
@@ -100,7 +128,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
   __shared__ __align__(8) unsigned long long full[V1_STAGES], empty[V1_STAGES];
   __shared__ V1Tile desc[V1_STAGES];
   unsigned char* raw = v1_smem;                                              // [V1_STAGES][raw_bytes]
-  double2* W = reinterpret_cast<double2*>(v1_smem + (size_t)V1_STAGES * a.raw_bytes);   // [NFU][len]
+  double2* W = reinterpret_cast<double2*>(v1_smem + (size_t)a.stages * a.raw_bytes);   // [len][NFU]
   uint16_t* codes = reinterpret_cast<uint16_t*>(W + (size_t)NFU * a.len);    // [S]
   const int tid = threadIdx.x;
   const uint32_t q = (a.n_tiles + gridDim.x - 1) / gridDim.x;
@@ -110,12 +138,15 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 #pragma unroll
     for (int s = 0; s < V1_STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s + 8 * s));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty_s + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_s + 8 * s), "n"(V1_THREADS / 32));   // one arrive per consumer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < V1_THREADS)
-    for (int i = tid; i < NFU * a.len; i += V1_THREADS) W[i] = (i < a.nfu * a.len) ? __ldg(&a.table[i]) : make_double2(0.0, 0.0);
+    for (int i = tid; i < NFU * a.len; i += V1_THREADS) {                       // W[j][m] <- table[m][j], absent rows zero
+      const int j = i / NFU, m = i - j * NFU;
+      W[i] = (m < a.nfu) ? __ldg(&a.table[m * a.len + j]) : make_double2(0.0, 0.0);
+    }
   __syncthreads();
 
   if (tid >= V1_THREADS) {
@@ -128,8 +159,8 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
     int k0 = (int)(t_begin - __ldg(&a.tile_first[rec])) * a.S;
     for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
       while (k0 >= pl.nsym) { pl = a.plans[++rec]; k0 = 0; }                 // next recording that has symbols
-      const int st = i % V1_STAGES;
-      if (i >= V1_STAGES) mbar_wait(empty_s + 8 * st, ((i / V1_STAGES) - 1) & 1);
+      const int st = i % a.stages;
+      if (i >= (uint32_t)a.stages) mbar_wait<true>(empty_s + 8 * st, ((i / a.stages) - 1) & 1);
       const int ns = min(a.S, pl.nsym - k0);
       // bytes [b0, b1) of the batch buffer, widened to 16-byte boundaries (never past the buffer's last whole 16 bytes)
       const uint64_t b0 = (pl.off + (uint64_t)k0 * a.sps) * sizeof(TIn), b1 = b0 + (uint64_t)ns * a.sps * sizeof(TIn);
@@ -158,10 +189,11 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
   }
 
   // ================================ consumers (V1_THREADS threads) ================================
-  const int G = a.G, SP = V1_THREADS / G, grp = tid / G, l = tid - grp * G;
+  const int G = a.G, SP = V1_THREADS / G, grp = tid / G, l = tid - grp * G, lane = tid & 31;
+  const bool fast = (G == 1) && (32 % a.bpsym == 0);          // thread per symbol, whole words per warp: no CTA barrier at all
   for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
-    const int st = i % V1_STAGES;
-    mbar_wait(full_s + 8 * st, (i / V1_STAGES) & 1);
+    const int st = i % a.stages;
+    mbar_wait<false>(full_s + 8 * st, (i / a.stages) & 1);
     const V1Tile d = desc[st];
     const unsigned char* xs = raw + (size_t)st * a.raw_bytes + d.skew;
     const int ns = d.ns;
@@ -172,12 +204,44 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 #pragma unroll
       for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
       if (valid) {
-        const int base = s * a.sps + a.off0;
-#pragma unroll 2
-        for (int j = l; j < a.len; j += G) {
-          const double x = smem_sample_d<TIn>(xs, base + j);
+        const TIn* xp = reinterpret_cast<const TIn*>(xs) + (s * a.sps + a.off0);
+        if (G == 1) {                                  // thread per symbol: weights are broadcast loads
+          const double2* wp = W;
+          int j = 0;
+          if (a.len % 5 == 0) {
+            for (; j < a.len; j += 5) {
 #pragma unroll
-          for (int m = 0; m < NFU; ++m) { const double2 w = W[m * a.len + j]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+              for (int u = 0; u < 5; ++u) {
+                const double x = smem_sample_d<TIn>(reinterpret_cast<const unsigned char*>(xp), u);
+#pragma unroll
+                for (int m = 0; m < NFU; ++m) { const double2 w = wp[u * NFU + m]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+              }
+              xp += 5; wp += 5 * NFU;
+            }
+          } else {
+            for (; j + 4 <= a.len; j += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const double x = smem_sample_d<TIn>(reinterpret_cast<const unsigned char*>(xp), u);
+#pragma unroll
+                for (int m = 0; m < NFU; ++m) { const double2 w = wp[u * NFU + m]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+              }
+              xp += 4; wp += 4 * NFU;
+            }
+            for (; j < a.len; ++j) {
+              const double x = smem_sample_d<TIn>(reinterpret_cast<const unsigned char*>(xp), 0);
+#pragma unroll
+              for (int m = 0; m < NFU; ++m) { const double2 w = wp[m]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+              ++xp; wp += NFU;
+            }
+          }
+        } else {
+#pragma unroll 4
+          for (int j = l; j < a.len; j += G) {
+            const double x = smem_sample_d<TIn>(reinterpret_cast<const unsigned char*>(xp), j);
+#pragma unroll
+            for (int m = 0; m < NFU; ++m) { const double2 w = W[j * NFU + m]; fr[m] = fma(x, w.x, fr[m]); fi[m] = fma(x, w.y, fi[m]); }
+          }
         }
       }
       for (int off = G >> 1; off > 0; off >>= 1) {
@@ -187,62 +251,65 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
           fi[m] += __shfl_xor_sync(0xffffffffu, fi[m], off);
         }
       }
+      uint32_t code = 0;
       if (valid && l == 0) {
-        uint32_t code;
-        switch (a.mode) {
-          case V1_BPSK: code = fr[0] > 0.0 ? 0u : 1u; break;                    // B.4: '0' if I > 0 else '1'
-          case V1_QPSK: code = quadrant_code(fr[0], fi[0]); break;
-          case V1_PSK8: code = psk8_code(fr[0], fi[0]); break;
-          case V1_OFDM: {                                                        // B.7: bins in order, 2 bits each
-            code = 0;
-            for (int m = 0; m < a.nf; ++m) {
-              const int r = a.map[m] & 0xff;
-              double re = 0.0, im = 0.0;
+        if (a.mode == V1_QPSK) code = quadrant_code(fr[0], fi[0]);              // B.5
+        else if (a.mode == V1_BPSK) code = fr[0] > 0.0 ? 0u : 1u;               // B.4: '0' if I > 0 else '1'
+        else if (a.mode == V1_PSK8) code = psk8_code(fr[0], fi[0]);
+        else if (a.mode == V1_OFDM) {                                           // B.7: bins in order, 2 bits each
+          uint32_t qq = 0, qc = 0;                                              // quadrant of each unique bin / of its conjugate
 #pragma unroll
-              for (int u = 0; u < NFU; ++u) if (u == r) { re = fr[u]; im = fi[u]; }
-              if (a.map[m] & 0x100) im = -im;                                    // F[L - m] = conj(F[m]) for real input
-              code = (code << 2) | quadrant_code(re, im);
-            }
-            break;
+          for (int u = 0; u < NFU; ++u) {
+            qq |= quadrant_code(fr[u], fi[u]) << (2 * u);
+            qc |= quadrant_code(fr[u], -fi[u]) << (2 * u);                      // F[L - m] = conj(F[m]) for real input
           }
-          default: {                                                             // V1_FSK: bit = p_mark > p_space
-            constexpr int I1 = NFU > 1 ? 1 : 0;
-            const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
-            code = pm > ps ? 1u : 0u;
+          for (int m = 0; m < a.nf; ++m) {
+            const int mp = a.map[m];
+            code = (code << 2) | ((((mp & 0x100) ? qc : qq) >> (2 * (mp & 0xff))) & 3u);
           }
+        } else {                                                                // V1_FSK: bit = p_mark > p_space
+          constexpr int I1 = NFU > 1 ? 1 : 0;
+          const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
+          code = pm > ps ? 1u : 0u;
         }
+      }
+      if (fast) {
+        // 32 consecutive symbols of this warp = bpsym whole words: OR-reduce the shifted codes (redux.sync), lane k stores word k
+        const int spw = 32 / a.bpsym, kw = lane / spw;
+        const uint32_t v = code << (32 - a.bpsym * ((lane - kw * spw) + 1));
+        uint32_t mine = 0;
+        for (int k = 0; k < a.bpsym; ++k) {
+          const uint32_t wk = __reduce_or_sync(0xffffffffu, kw == k ? v : 0u);
+          if (lane == k) mine = wk;
+        }
+        const int sw = s0 + (tid & ~31);                                        // first symbol of this warp's 32
+        if (lane < a.bpsym && sw + lane * spw < ns)
+          v1_store_word(a, d, ((uint64_t)(d.k0 + sw) * a.bpsym) / 32 + lane, mine);
+      } else if (valid && l == 0) {
         codes[s] = (uint16_t)code;
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");               // codes complete; the stage's samples are consumed
-    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8 * st) : "memory");
-    // ---- pack: ns * bpsym bits, 32 per thread, big-endian words ------------------------------------------------
-    const int nwords = (ns * a.bpsym + 31) / 32;
-    for (int w = tid; w < nwords; w += V1_THREADS) {
-      uint32_t word = 0;
-      int sym = (w * 32) / a.bpsym, pos = (w * 32) - sym * a.bpsym;
-      uint32_t cur = sym < ns ? codes[sym] : 0u;
-#pragma unroll 8
-      for (int b = 0; b < 32; ++b) {
-        word = (word << 1) | ((cur >> (a.bpsym - 1 - pos)) & 1u);
-        if (++pos == a.bpsym) { pos = 0; ++sym; cur = sym < ns ? codes[sym] : 0u; }
-      }
-      const uint64_t widx = (uint64_t)d.k0 * a.bpsym / 32 + w;
-      if (a.to_workspace) {
-        a.bits[d.word_off + widx] = __byte_perm(word, 0, 0x0123);
-      } else {
-        const uint64_t nbytes = min((uint64_t)d.nsym * a.bpsym / 8, d.out_cap);   // truncate to a multiple of 8 bits
-        uint8_t* o = a.out + d.out_off;
-        if (widx * 4 + 4 <= nbytes) {
-          *reinterpret_cast<uint32_t*>(o + widx * 4) = __byte_perm(word, 0, 0x0123);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (widx * 4 + k < nbytes) o[widx * 4 + k] = (uint8_t)(word >> (24 - 8 * k));
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8 * st) : "memory");   // stage consumed by this warp
+    if (!fast) {
+      asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");             // codes complete
+      // ---- pack: ns * bpsym bits, 32 per thread, big-endian words ----------------------------------------------
+      const int nwords = (ns * a.bpsym + 31) / 32;
+      for (int w = tid; w < nwords; w += V1_THREADS) {
+        // symbols sym, sym+1, ... appended MSB-first into a 64-bit shifter until 32 bits of this word are in
+        int sym = (w * 32) / a.bpsym;
+        const int skip = (w * 32) - sym * a.bpsym;     // leading bits of `sym` that belong to the previous word
+        unsigned long long acc = (sym < ns ? codes[sym] : 0u) & ((1u << (a.bpsym - skip)) - 1u);
+        int have = a.bpsym - skip;
+        while (have < 32) {
+          ++sym;
+          acc = (acc << a.bpsym) | (unsigned long long)(sym < ns ? codes[sym] : 0u);
+          have += a.bpsym;
         }
+        v1_store_word(a, d, (uint64_t)d.k0 * a.bpsym / 32 + w, (uint32_t)(acc >> (have - 32)));
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");             // codes may be overwritten by the next tile
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");               // codes may be overwritten by the next tile
   }
 }
 
@@ -396,11 +463,22 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   // ---- tile geometry: G lanes per symbol, S symbols (multiple of 32) per tile, ~12 KB of samples per tile
   // (the pre-filtered FSK path always correlates float32)
   const size_t kesz = p.prefilter ? 4 : esz;
+  // lanes per symbol: thread t of a symbol group reads element t + G*i of its symbol; with c = largest power of two
+  // dividing sps the reads of a warp hit banks c/G-way -- up to 4-way is cheaper than widening the shuffle reduction
   int G = 1;
   while (G < 32 && p.sps % (2 * G) == 0) G *= 2;
-  int S = (int)std::max<size_t>(32, std::min<size_t>(1024, (12288 / ((size_t)p.sps * kesz)) / 32 * 32));
+  G = std::max(1, G / 4);
+  while (G > 1 && p.len / G < 4) G /= 2;
+  size_t tile_target = 20480;
+  int stages = 3;
+  if (const char* e = getenv("FB_V1_TILE")) tile_target = (size_t)std::max(1024, atoi(e));      // tuning knobs
+  if (const char* e = getenv("FB_V1_STAGES")) stages = std::max(2, std::min(V1_STAGES, atoi(e)));
+  // whole passes of the 256 consumer threads (V1_THREADS / G symbols each), so no pass runs with idle warps
+  const int SP = std::max(32, V1_THREADS / G);
+  int S = (int)std::min<size_t>(4096, (tile_target / ((size_t)p.sps * kesz)) / SP * SP);
+  if (S < SP) S = (int)std::max<size_t>(32, std::min<size_t>(SP, (tile_target / ((size_t)p.sps * kesz)) / 32 * 32));
   const size_t raw_bytes = ((size_t)S * p.sps * kesz + 16 + 127) / 128 * 128;
-  const size_t smem = V1_STAGES * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
+  const size_t smem = stages * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
   if (smem > 200 * 1024) return FB_EUNSUPPORTED;
   std::vector<RecPlan> plans(n_rec);
   std::vector<uint32_t> tile_first(n_rec + 1, 0);
@@ -474,7 +552,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   a.n_rec = n_rec; a.mode = p.mode; a.sps = p.sps; a.off0 = p.off0; a.len = p.len; a.nf = p.nf; a.bpsym = p.bits_per_sym;
   a.to_workspace = p.uart ? 1 : 0;
   a.nfu = nfu; a.G = G; a.S = S; a.raw_bytes = (int)raw_bytes;
-  a.total_bytes = (uint64_t)total_samples * kesz; a.n_tiles = n_tiles;
+  a.total_bytes = (uint64_t)total_samples * kesz; a.n_tiles = n_tiles; a.stages = stages;
   for (int m = 0; m < 8; ++m) a.map[m] = map[m];
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));

@@ -8,8 +8,14 @@ nsamp = float(sys.argv[4]) if len(sys.argv) > 4 else None
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 sass = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
-mangled_hint = rows[0][1]
-hdr = rows[1]; data = rows[2:]
+# several launches may be in the report: take the LAST one whose (demangled) name contains argv[6] (default: first launch)
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+pick = sys.argv[6] if len(sys.argv) > 6 else None
+cand = [i for i in starts if pick is None or pick in rows[i][1]]
+i0 = cand[-1] if pick else cand[0]
+i1 = min([j for j in starts if j > i0] + [len(rows)])
+mangled_hint = rows[i0][1]
+hdr = rows[i0 + 1]; data = [r for r in rows[i0 + 2:i1] if r]
 ia, isamp, iaddr, isrc = hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('Address'), hdr.index('Source')
 base = int(data[0][iaddr], 16)
 tmp = tempfile.mkdtemp()
