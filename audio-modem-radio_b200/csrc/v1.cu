@@ -32,6 +32,7 @@ struct V1Args {
   int raw_bytes;                 // shared-memory bytes reserved for one staged tile (multiple of 128)
   uint32_t n_tiles;
   int stages;
+  int lg_spw;                    // log2(32 / bpsym) when bpsym divides 32 (whole words per warp), else -1
   int map[8];                    // bin m -> unique row (bits 0-7), conjugate flag (bit 8)
 };
 
@@ -157,10 +158,12 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
     int rec = lo;
     RecPlan pl = a.plans[rec];
     int k0 = (int)(t_begin - __ldg(&a.tile_first[rec])) * a.S;
-    for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
+    int st = 0;
+    uint32_t ph = 1;                                                        // parity of the previous round of `empty`
+    bool wrapped = false;
+    for (uint32_t t = t_begin; t < t_end; ++t) {
       while (k0 >= pl.nsym) { pl = a.plans[++rec]; k0 = 0; }                 // next recording that has symbols
-      const int st = i % a.stages;
-      if (i >= (uint32_t)a.stages) mbar_wait<true>(empty_s + 8 * st, ((i / a.stages) - 1) & 1);
+      if (wrapped) mbar_wait<true>(empty_s + 8 * st, ph);
       const int ns = min(a.S, pl.nsym - k0);
       // bytes [b0, b1) of the batch buffer, widened to 16-byte boundaries (never past the buffer's last whole 16 bytes)
       const uint64_t b0 = (pl.off + (uint64_t)k0 * a.sps) * sizeof(TIn), b1 = b0 + (uint64_t)ns * a.sps * sizeof(TIn);
@@ -184,16 +187,18 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
       }
       k0 += a.S;
+      if (++st == a.stages) { st = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
     }
     return;
   }
 
   // ================================ consumers (V1_THREADS threads) ================================
   const int G = a.G, SP = V1_THREADS / G, grp = tid / G, l = tid - grp * G, lane = tid & 31;
-  const bool fast = (G == 1) && (32 % a.bpsym == 0);          // thread per symbol, whole words per warp: no CTA barrier at all
-  for (uint32_t t = t_begin, i = 0; t < t_end; ++t, ++i) {
-    const int st = i % a.stages;
-    mbar_wait<false>(full_s + 8 * st, (i / a.stages) & 1);
+  const bool fast = (G == 1) && (a.lg_spw >= 0);          // thread per symbol, whole words per warp: no CTA barrier at all
+  int st = 0;
+  uint32_t ph = 0;
+  for (uint32_t t = t_begin; t < t_end; ++t) {
+    mbar_wait<false>(full_s + 8 * st, ph);
     const V1Tile d = desc[st];
     const unsigned char* xs = raw + (size_t)st * a.raw_bytes + d.skew;
     const int ns = d.ns;
@@ -275,8 +280,8 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
       }
       if (fast) {
         // 32 consecutive symbols of this warp = bpsym whole words: OR-reduce the shifted codes (redux.sync), lane k stores word k
-        const int spw = 32 / a.bpsym, kw = lane / spw;
-        const uint32_t v = code << (32 - a.bpsym * ((lane - kw * spw) + 1));
+        const int spw = 1 << a.lg_spw, kw = lane >> a.lg_spw;
+        const uint32_t v = code << (32 - a.bpsym * ((lane & (spw - 1)) + 1));
         uint32_t mine = 0;
         for (int k = 0; k < a.bpsym; ++k) {
           const uint32_t wk = __reduce_or_sync(0xffffffffu, kw == k ? v : 0u);
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
         }
         const int sw = s0 + (tid & ~31);                                        // first symbol of this warp's 32
         if (lane < a.bpsym && sw + lane * spw < ns)
-          v1_store_word(a, d, ((uint64_t)(d.k0 + sw) * a.bpsym) / 32 + lane, mine);
+          v1_store_word(a, d, ((uint64_t)(d.k0 + sw) >> a.lg_spw) + lane, mine);
       } else if (valid && l == 0) {
         codes[s] = (uint16_t)code;
       }
@@ -310,6 +315,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
       }
       asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");             // codes may be overwritten by the next tile
     }
+    if (++st == a.stages) { st = 0; ph ^= 1u; }
   }
 }
 
@@ -470,7 +476,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   G = std::max(1, G / 4);
   while (G > 1 && p.len / G < 4) G /= 2;
   size_t tile_target = 20480;
-  int stages = 3;
+  int stages = 2;
   if (const char* e = getenv("FB_V1_TILE")) tile_target = (size_t)std::max(1024, atoi(e));      // tuning knobs
   if (const char* e = getenv("FB_V1_STAGES")) stages = std::max(2, std::min(V1_STAGES, atoi(e)));
   // whole passes of the 256 consumer threads (V1_THREADS / G symbols each), so no pass runs with idle warps
@@ -553,6 +559,8 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   a.to_workspace = p.uart ? 1 : 0;
   a.nfu = nfu; a.G = G; a.S = S; a.raw_bytes = (int)raw_bytes;
   a.total_bytes = (uint64_t)total_samples * kesz; a.n_tiles = n_tiles; a.stages = stages;
+  a.lg_spw = -1;
+  for (int k = 0; k <= 5; ++k) if ((32 >> k) == p.bits_per_sym) a.lg_spw = k;
   for (int m = 0; m < 8; ++m) a.map[m] = map[m];
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
