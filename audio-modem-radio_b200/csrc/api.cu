@@ -64,8 +64,12 @@ extern "C" fb_handle* fb_create(int device) {
   fb_handle* h = new fb_handle();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  // stream2 carries the small latency-bound edge kernels that run beside the big interior kernels: it gets the highest
+  // priority so its few CTAs are placed as soon as resources free up instead of after the interior grid has drained
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess) {

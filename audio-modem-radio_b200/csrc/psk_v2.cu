@@ -717,11 +717,11 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-  if (ea.n_jobs > 0) {
+  if (ea.n_jobs > 0 && !getenv("FB_DEBUG_NO_EDGE")) {
     psk_edge_kernel<TIn><<<(ea.n_jobs + 31) / 32, 32, 0, h->stream2>>>(ea);
     h->launches++;
   }
-  if (n_tiles > 0) {
+  if (n_tiles > 0 && !getenv("FB_DEBUG_NO_MAIN")) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
 #define FB_LAUNCH_MAIN(NTV, SPSV)                                                                                               \
