@@ -45,7 +45,7 @@ struct fb_handle {
   uint64_t launches = 0;
   std::string err;
   // device workspace (grown on demand, never shrunk)
-  DevBuf in, out, out_len, sync_idx, status, bits, plans, tile_first, jobs, scratch, taps, slow_w, sync_raw;
+  DevBuf in, out, out_len, sync_idx, status, bits, plans, tile_first, tiles, jobs, scratch, taps, slow_w, sync_raw;
   DevBuf fec_in, fec_out, fec_meta, misc;
   // host copy of the last PSK plan (fb_psk_last_bits)
   std::vector<RecPlan> last_plans;

@@ -26,13 +26,34 @@
 #define PM_MAXTAB 3712       // float2 entries of the per-launch constant table (taps + slow-pole row weights)
 #define SLOW_TBL 48          // per pole pair: 32 lane powers, 5 warp-scan multipliers, 9 warp powers (float2 each)
 
+// One main-kernel tile, resolved once per call by psk_tiles_kernel so that a CTA starts with ONE coalesced 32-byte load
+// instead of a dependent search (tile_first -> tile_first -> plans).
+struct __align__(16) PskTile {
+  uint64_t off, n, word_off;    // the recording: first sample (elements), samples, first word of its bit stream
+  int32_t d0, d1;               // differential symbols [d0, d1) of this tile; symbols d0 .. d1
+};
+
+__global__ void __launch_bounds__(256) psk_tiles_kernel(const RecPlan* plans, const uint32_t* tile_first, int n_rec, uint32_t n_tiles,
+                                                         int T, PskTile* tiles) {
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  int lo = 0, hi = n_rec;                             // largest r with tile_first[r] <= tile
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(&tile_first[mid]) <= tile) lo = mid; else hi = mid; }
+  const RecPlan pl = plans[lo];
+  PskTile t;
+  t.off = pl.off; t.n = pl.n; t.word_off = pl.word_off;
+  t.d0 = pl.dl32 + (int)(tile - __ldg(&tile_first[lo])) * T;
+  t.d1 = min(t.d0 + T, pl.dr32);
+  tiles[tile] = t;
+}
+
 // Per-launch arguments live in the kernel parameter space (constant bank 0): the FIR taps and the slow-pole row
 // weights are read as FFMA2 uniform-register operands (LDCU.64 c[0x0][..]), so the inner loop has no tap loads
 // through the LSU and nothing is shared between handles / streams.
 struct PskMainArgs {
   const void* samples;
-  const RecPlan* plans;
-  const uint32_t* tile_first;   // n_rec + 1 prefix of main tiles
+  const PskTile* tiles;         // one descriptor per CTA
+  uint32_t n_tiles, pf_dist;    // pf_dist: the tile this many CTAs ahead gets its samples prefetched into L2
   const float4* slow_pw4;       // [pairs][wpad]  {p_a^k, p_b^k}, zero for k > wlen: weights of the tile-boundary state sums (global)
   int wpad;                     // entries per pole pair in slow_pw4 (>= wlen + 1 + 1024, so over-reads hit zeros)
   const float2* slow_tbl;       // [nslow][SLOW_TBL]  powers of m = lam^PM_CH used by the column scan (global)
@@ -97,21 +118,10 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
   const int sps = SPS ? SPS : a.sps;
   constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
-  // ---- which recording / tile: largest r with tile_first[r] <= tile (32-way splitter search) -------------
+  // ---- this CTA's tile ---------------------------------------------------------------------------------------
   const uint32_t tile = blockIdx.x;
-  int lo = 0, hi = a.n_rec;
-  while (hi - lo > 1) {
-    const int step = (hi - lo + 31) >> 5;
-    const int probe = lo + (lane + 1) * step;
-    const bool le = probe < hi && __ldg(&a.tile_first[probe]) <= tile;
-    const int cnt = __popc(__ballot_sync(0xffffffffu, le));       // probes are monotone: the first cnt satisfy it
-    const int nlo = lo + cnt * step;
-    hi = min(hi, nlo + step);
-    lo = nlo;
-  }
-  const RecPlan pl = a.plans[lo];
-  const int d0 = pl.dl32 + (int)(tile - __ldg(&a.tile_first[lo])) * a.T;
-  const int d1 = min(d0 + a.T, pl.dr32);
+  const PskTile pl = a.tiles[tile];
+  const int d0 = pl.d0, d1 = pl.d1;
   const int ns = d1 - d0 + 1;                       // symbols d0 .. d1
   const int64_t N = (int64_t)pl.n;
   float* X = smem;                                  // [sps][P]   X[j][c] = x[n0 + (ca + c) sps + j]
@@ -181,6 +191,17 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
       }
     }
   }
+  // ---- L2 prefetch for the CTA that will run about one tile-time from now (same SM slot, pf_dist tiles ahead): its
+  // staging and boundary loads then hit L2 instead of paying the DRAM latency
+  if (tile + a.pf_dist < a.n_tiles) {
+    const PskTile nx = a.tiles[tile + a.pf_dist];
+    const int64_t p0 = max((int64_t)0, (int64_t)a.n0 + (int64_t)(nx.d0 - a.dh - PADL) * sps - a.wlen);
+    const int64_t p1 = min((int64_t)nx.n, (int64_t)a.n0 + (int64_t)(nx.d1 + 2 + a.dl) * sps + a.wlen);
+    const char* base = reinterpret_cast<const char*>(a.samples) + (nx.off + (uint64_t)p0) * sizeof(TIn);
+    const int64_t nbytes = (p1 - p0) * (int64_t)sizeof(TIn);
+    for (int64_t b = (int64_t)tid * 128; b < nbytes; b += (int64_t)nthr * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+  }
   // ---- exact start state of the forward slow recursion at column 0 (left record edge) ----------
   const bool near_left = (n_d0 - a.wlen) <= (int64_t)a.n0;          // the boundary sum would reach column 0
   if (near_left && tid < a.nslow) {
@@ -215,22 +236,28 @@ __global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_co
       const int cntb = (int)max((int64_t)0, min((int64_t)a.wlen + 1, N - n_e1));
       const int klo = fwd ? 1 : 0, khi = fwd ? cntf : cntb - 1;
       float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
-      for (int k0 = klo + 4 * (slice * 32 + lane); k0 <= khi; k0 += 512) {
-        float xv[4];
-        float4 w[4];
+      // three 512-sample steps per trip with all their loads in flight together (wlen is ~1200-1800 samples)
+      for (int k00 = klo + 4 * (slice * 32 + lane); k00 <= khi; k00 += 3 * 512) {
+        float xv[3][4];
+        float4 w[3][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = min(k0 + u, khi);                         // clamped address; the duplicate is zeroed below
-          const int64_t n = fwd ? n_d0 - k : n_e1 + k;
-          xv[u] = load_sample<TIn>(a.samples, pl.off + (uint64_t)n);
-          w[u] = __ldg(&pw[k0 + u]);
-        }
+        for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float x = (k0 + u <= khi) ? xv[u] : 0.f;
-          bs0 = bfma(x, make_float2(w[u].x, w[u].y), bs0);
-          bs1 = bfma(x, make_float2(w[u].z, w[u].w), bs1);
-        }
+          for (int u = 0; u < 4; ++u) {
+            const int kk = k00 + 512 * q + u;
+            const int k = min(kk, khi);                           // clamped address; the duplicate is zeroed below
+            const int64_t n = fwd ? n_d0 - k : n_e1 + k;
+            xv[q][u] = load_sample<TIn>(a.samples, pl.off + (uint64_t)n);
+            w[q][u] = __ldg(&pw[min(kk, a.wpad - 1)]);
+          }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float x = (k00 + 512 * q + u <= khi) ? xv[q][u] : 0.f;
+            bs0 = bfma(x, make_float2(w[q][u].x, w[q][u].y), bs0);
+            bs1 = bfma(x, make_float2(w[q][u].z, w[q][u].w), bs1);
+          }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -906,7 +933,16 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     FB_CUDA(h, cudaMemcpyAsync(tabs, pwv.data(), pwv.size() * 4, cudaMemcpyHostToDevice, h->stream));
     FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
-    ma.samples = d_samples; ma.plans = (const RecPlan*)h->plans.p; ma.tile_first = (const uint32_t*)h->tile_first.p;
+    if ((rc = fb_ensure(h, h->tiles, (size_t)std::max<uint32_t>(1, n_tiles) * sizeof(PskTile)))) return rc;
+    if (n_tiles > 0) {
+      psk_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>((const RecPlan*)h->plans.p, (const uint32_t*)h->tile_first.p, n_rec,
+                                                                      n_tiles, T, (PskTile*)h->tiles.p);
+      h->launches++;
+    }
+    ma.samples = d_samples; ma.tiles = (const PskTile*)h->tiles.p; ma.n_tiles = n_tiles;
+    ma.pf_dist = (uint32_t)(2 * h->sm_count);        // resident CTAs: two per SM
+    ma.pf_dist = 0x7fffffffu;                        // measured: the prefetch costs more than it hides (2 CTAs/SM already overlap)
+    if (const char* e = getenv("FB_PSK_PF")) { if (atoi(e) > 0) ma.pf_dist = (uint32_t)atoi(e); }   // tuning knob
     ma.slow_pw4 = (const float4*)tabs; ma.wpad = wpad; ma.slow_tbl = (const float2*)(tabs + o_tb); ma.bits = (uint32_t*)h->bits.p;
     ma.n_rec = n_rec; ma.sps = d.sps; ma.n0 = d.n0; ma.bps = bps; ma.nt = d.nt; ma.ntp = ntp; ma.dl = d.dl; ma.dh = d.dh;
     ma.nslow = d.nslow; ma.wlen = wlen; ma.pad_bp = d.pad_bp; ma.T = T; ma.P = P; ma.padl = padl;

@@ -44,7 +44,7 @@ from scipy import signal
 MAX_SLOW = 4           # conjugate pole pairs handled by the recursive path (band-pass has 4 pairs)
 MAX_TAPS = 8192        # complex taps (NT * sps) the FIR table can hold
 FIR_TOL = 1.0e-7       # relative size of the neglected fast tail (actual is 6e-9..3e-8 after rounding NT up; fp32 evaluation adds ~1e-7)
-SLOW_TOL = 1.0e-9      # warm-up truncation of the slow recursion, relative
+SLOW_TOL = 1.0e-8      # warm-up truncation of the slow recursion: neglected state, relative to max|c| (residue size included)
 EDGE_TOL = 1.0e-10     # decay demanded before the interior formula takes over from the edge kernel
 
 
@@ -237,7 +237,8 @@ def psk_design(baud: float, carrier: float, samp_rate: float, band_k: float, n0_
                 arr = getattr(cs, name)
                 arr[2 * i], arr[2 * i + 1] = v.real, v.imag
             r_slow = max(r_slow, abs(p))
-        d.wcols = 0 if not res else -(-_decay_len(r_slow, SLOW_TOL) // sps)
+        # truncating the boundary sums after w samples leaves |R| r^w of the state: size it against max|c| like the FIR tail
+        d.wcols = 0 if not res else -(-_decay_len(r_slow, min(0.5, SLOW_TOL / max(cond, 1e-12))) // sps)
         # interior formula valid for symbols with  zone_left <= n_k <= N-1-zone_right
         d.zone_left = max(hpos, d.w_lp)
         d.zone_right = max(hneg, d.w_lp) + d.w_bp

@@ -7,10 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "audio-modem-radio_b200")]
 import torch, fbdsp
 from fbdsp import _lib
-ap = argparse.ArgumentParser(); ap.add_argument("--recordings", type=int, default=256); ap.add_argument("--dtype", default="f32")
+ap = argparse.ArgumentParser(); ap.add_argument("--recordings", type=int, default=256); ap.add_argument("--dtype", default="f32"); ap.add_argument("--carrier", type=float, default=9600.0)
 args = ap.parse_args()
 dev = torch.device("cuda", 0); eng = fbdsp.Engine(0)
-d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+d = fbdsp.psk_design(9600.0, args.carrier, 96000.0, 1.5, False)
 n_rec, n = args.recordings, 180 * 96000
 if args.dtype == "f32":
     batch = torch.randn(n_rec * n, device=dev, dtype=torch.float32) * 0.3; dt = _lib.FB_F32
