@@ -23,6 +23,9 @@
 
 #define PM_CH 8              // columns (= symbols) per thread: FIR register tile and slow-pole scan chunk
 #define PM_THREADS 256
+#ifndef PM_MINB
+#define PM_MINB 2
+#endif
 #define PM_MAXTAB 3712       // float2 entries of the per-launch constant table (taps + slow-pole row weights)
 #define SLOW_TBL 48          // per pole pair: 32 lane powers, 5 warp-scan multipliers, 9 warp powers (float2 each)
 
@@ -108,7 +111,7 @@ __device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2);
 // SPS > 0: samples per symbol known at compile time (even; float32 input): the staging loop is fully unrolled with all
 // of a thread's loads in flight before the first store; SPS == 0: runtime sps.
 template <typename TIn, int NT, int SPS>
-__global__ void __launch_bounds__(PM_THREADS, 2) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
+__global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
   __shared__ float2 s_tot[8][4];         // warp totals of the column scan [warp][seq]
@@ -744,11 +747,11 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-  if (ea.n_jobs > 0 && !getenv("FB_DEBUG_NO_EDGE")) {
+  if (ea.n_jobs > 0) {
     psk_edge_kernel<TIn><<<(ea.n_jobs + 31) / 32, 32, 0, h->stream2>>>(ea);
     h->launches++;
   }
-  if (n_tiles > 0 && !getenv("FB_DEBUG_NO_MAIN")) {
+  if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
 #define FB_LAUNCH_MAIN(NTV, SPSV)                                                                                               \

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(FB_THREADS) v1_finish_kernel(const RecPlan* pl
 // scipy filtfilt (order <= 8, float64), chunk-parallel exactly like fsk_v2.cu; output cast to float32 (B.2: the v1 code
 // re-casts the filtered record to float32 before the Goertzel loop).
 #define PF_ORD 8
-#define PF_CHUNK 2048
+#define PF_CHUNK 1024
 struct PfFilt { double b[PF_ORD + 1], a[PF_ORD + 1], zi[PF_ORD]; int32_t w, pad; };
 
 template <typename TIn>
@@ -368,7 +368,14 @@ __device__ __forceinline__ double pf_x_ext(const void* samples, uint64_t off, in
 }
 
 template <typename TIn>
-__global__ void __launch_bounds__(64) pf_fwd_kernel(const void* samples, uint64_t off, int64_t N, PfFilt t, double* yfwd) {
+// grid.y = recording of the group (all recordings of a group run in ONE launch: a single 3-minute recording is only
+// ~17 k chunk-threads, far too few to fill 148 SMs); yoff[r] = first double of recording r's forward-pass scratch
+__global__ void __launch_bounds__(64) pf_fwd_kernel(const void* samples, const RecPlan* plans, const uint64_t* yoff, PfFilt t, double* ybase) {
+  const RecPlan pl = plans[blockIdx.y];
+  if (pl.status != FB_ST_OK) return;
+  const uint64_t off = pl.off;
+  const int64_t N = (int64_t)pl.n;
+  double* yfwd = ybase + yoff[blockIdx.y];
   const int64_t Next = N + 2 * t.pad;
   const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PF_CHUNK;
   if (c0 >= Next) return;
@@ -393,7 +400,12 @@ __global__ void __launch_bounds__(64) pf_fwd_kernel(const void* samples, uint64_
   }
 }
 
-__global__ void __launch_bounds__(64) pf_bwd_kernel(const double* yfwd, int64_t N, PfFilt t, float* f32) {
+__global__ void __launch_bounds__(64) pf_bwd_kernel(const double* ybase, const RecPlan* plans, const uint64_t* yoff, PfFilt t, float* fbase) {
+  const RecPlan pl = plans[blockIdx.y];
+  if (pl.status != FB_ST_OK) return;
+  const int64_t N = (int64_t)pl.n;
+  const double* yfwd = ybase + yoff[blockIdx.y];
+  float* f32 = fbase + pl.off;
   const int64_t Next = N + 2 * t.pad;
   const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PF_CHUNK;
   if (c0 >= Next) return;
@@ -530,23 +542,46 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
 
   int kdtype = dtype;
   if (p.prefilter) {
-    // filtered copy of the whole batch as float32 (B.2 casts the filtered record back to float32): scratch = [f32 batch][yfwd]
+    // filtered copy of the whole batch as float32 (B.2 casts the filtered record back to float32): scratch = [f32 batch]
+    // [yfwd of one group of recordings][yoff table].  Recordings are filtered in groups of up to ~4 GB of float64
+    // forward-pass scratch, every group in two launches (forward chunks, backward chunks).
     const size_t o_y = ((size_t)total_samples * 4 + 255) / 256 * 256;
-    if ((rc = fb_ensure(h, h->scratch, o_y + ((size_t)maxN + 2 * p.bp_pad + 16) * 8))) return rc;
+    const uint64_t group_doubles = std::max<uint64_t>((uint64_t)maxN + 2 * p.bp_pad + 16, (uint64_t)1 << 29);
+    const size_t o_t = o_y + ((size_t)std::min<uint64_t>(group_doubles, (uint64_t)total_samples + (uint64_t)n_rec * (2 * p.bp_pad + 16)) * 8 + 255) / 256 * 256;
+    if ((rc = fb_ensure(h, h->scratch, o_t + (size_t)n_rec * 8 + 16))) return rc;
     float* f32 = (float*)h->scratch.p;
     double* yfwd = (double*)((char*)h->scratch.p + o_y);
+    uint64_t* d_yoff = (uint64_t*)((char*)h->scratch.p + o_t);
     PfFilt t;
     for (int i = 0; i <= PF_ORD; ++i) { t.b[i] = p.bp_b[i]; t.a[i] = p.bp_a[i]; }
     for (int i = 0; i < PF_ORD; ++i) t.zi[i] = p.bp_zi[i];
     t.w = p.bp_w; t.pad = p.bp_pad;
-    for (int r = 0; r < n_rec; ++r) {
-      if (plans[r].status != FB_ST_OK) continue;
-      const int64_t N = (int64_t)plans[r].n, Next = N + 2 * p.bp_pad;
-      const int nthreads = (int)((Next + PF_CHUNK - 1) / PF_CHUNK), nblocks = (nthreads + 63) / 64;
-      if (dtype == FB_F32) pf_fwd_kernel<float><<<nblocks, 64, 0, h->stream>>>(d_samples, plans[r].off, N, t, yfwd);
-      else if (dtype == FB_F64) pf_fwd_kernel<double><<<nblocks, 64, 0, h->stream>>>(d_samples, plans[r].off, N, t, yfwd);
-      else pf_fwd_kernel<int16_t><<<nblocks, 64, 0, h->stream>>>(d_samples, plans[r].off, N, t, yfwd);
-      pf_bwd_kernel<<<nblocks, 64, 0, h->stream>>>(yfwd, N, t, f32 + plans[r].off);
+    std::vector<uint64_t> yoff(n_rec, 0);
+    std::vector<std::pair<int, int>> groups;               // [first, last) recordings per launch group
+    for (int r0 = 0; r0 < n_rec;) {
+      uint64_t used = 0;
+      int r1 = r0;
+      while (r1 < n_rec && r1 - r0 < 65535) {
+        const uint64_t need = plans[r1].n + 2 * (uint64_t)p.bp_pad + 16;
+        if (r1 > r0 && used + need > group_doubles) break;
+        yoff[r1] = used; used += need; ++r1;
+      }
+      groups.emplace_back(r0, r1);
+      r0 = r1;
+    }
+    FB_CUDA(h, cudaMemcpyAsync(d_yoff, yoff.data(), (size_t)n_rec * 8, cudaMemcpyHostToDevice, h->stream));
+    for (auto& gr : groups) {
+      int64_t gmax = 0;
+      for (int r = gr.first; r < gr.second; ++r) if (plans[r].status == FB_ST_OK) gmax = std::max<int64_t>(gmax, (int64_t)plans[r].n);
+      if (gmax == 0) continue;
+      const int64_t Next = gmax + 2 * p.bp_pad;
+      const int nthreads = (int)((Next + PF_CHUNK - 1) / PF_CHUNK);
+      const dim3 grid((nthreads + 63) / 64, gr.second - gr.first);
+      const RecPlan* gp = (const RecPlan*)h->plans.p + gr.first;
+      if (dtype == FB_F32) pf_fwd_kernel<float><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
+      else if (dtype == FB_F64) pf_fwd_kernel<double><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
+      else pf_fwd_kernel<int16_t><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
+      pf_bwd_kernel<<<grid, 64, 0, h->stream>>>(yfwd, gp, d_yoff + gr.first, t, f32);
       h->launches += 2;
     }
     d_samples = f32;
