@@ -159,6 +159,66 @@ def cpu_baseline(seconds_per_rec: int = 30, reps: int = 1):
                       f"one process per core"}
 
 
+# ----------------------------------------------------------------------------------------- other schemes
+def scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets, steps=3):
+    """Kernel-only throughput of the v1 streaming demodulators (north_star's named kernels) and the v2 aliases on the
+    batch already resident in HBM: whole C-ABI call timed with CUDA events on the engine stream."""
+    import ctypes
+    from fbdsp import _lib, modem_v1 as g
+    import fbdsp
+    dev = batch.device
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:      # noqa: BLE001
+        pass
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    flags = _lib.FB_SAMPLES_ON_DEVICE | _lib.FB_OUT_ON_DEVICE | _lib.FB_ASYNC
+    es = torch.cuda.ExternalStream(eng.stream, device=dev)
+    ol = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+    sy = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+    st = torch.zeros(n_rec, dtype=torch.int32, device=dev)
+    out = {}
+
+    def timed(name, f):
+        for _ in range(2):
+            f()
+        eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(es)
+        for _ in range(steps):
+            f()
+        e1.record(es)
+        eng.sync()
+        ms = e0.elapsed_time(e1) / steps
+        byt = n_rec * n_samp * 4 + int(ol.sum().item())
+        out[name] = {"ms": round(ms, 3), "gsamples_per_s": round(n_rec * n_samp / ms / 1e6, 1), "GBps": round(byt / ms / 1e6, 1),
+                     "frac_of_measured_hbm": round(byt / ms / 1e6 / peak, 4)}
+
+    for name, (p, table) in {"v1_qpsk_9600": g.psk_params(g.V1_QPSK, 9600, 9600.0), "v1_bpsk_9600": g.psk_params(g.V1_BPSK, 9600, 3000.0),
+                             "v1_ofdm8_9600": g.ofdm_params(9600, 8), "v1_ofdm4_4800": g.ofdm_params(4800, 4),
+                             "v1_psk8_2400": g.psk_params(g.V1_PSK8, 2400, 12000.0)}.items():
+        size = (int(eng.lib.fb_v1_out_bound(ctypes.byref(p), n_samp)) + 7) // 4 * 4
+        oo = np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(size)
+        buf = torch.empty(n_rec * size + 16, dtype=torch.uint8, device=dev)
+
+        def f(p=p, table=table, oo=oo, buf=buf):
+            rc = eng.lib.fb_v1_demod_batch(eng.handle, ctypes.byref(p), table.ctypes.data, n_rec, batch.data_ptr(), offsets.ctypes.data_as(u64p),
+                                           _lib.FB_F32, flags, buf.data_ptr(), oo.ctypes.data_as(u64p), ol.data_ptr(), st.data_ptr())
+            _lib.check(eng.lib, eng.handle, rc, "fb_v1_demod_batch")
+        timed(name, f)
+        del buf
+    for name, (baud, carrier, k, n0sps) in {"v2_qpsk_9600_c3000_gui_default": (9600, 3000.0, 1.5, False),
+                                            "v2_bpsk_4800_c9600": (4800, 9600.0, 1.0, True)}.items():
+        dd = fbdsp.psk_design(float(baud), float(carrier), float(FS), k, n0sps)
+        oo = eng.out_bounds(dd, [n_samp] * n_rec)
+        buf = torch.empty(int(oo[-1]) + 16, dtype=torch.uint8, device=dev)
+        timed(name, lambda dd=dd, oo=oo, buf=buf: eng.psk_demod_raw(dd, batch.data_ptr(), offsets, _lib.FB_F32, flags, buf.data_ptr(), oo,
+                                                                     ol.data_ptr(), sy.data_ptr(), st.data_ptr()))
+        del buf
+    return out
+
+
 # ----------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -172,6 +232,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-schemes", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -337,6 +398,39 @@ def main():
     except RuntimeError as e:       # pinned allocation can fail on a small host
         e2e = {"value": None, "unit": "Msamples/s", "error": str(e)[:200]}
 
+    # ---- e2e on PCM16 host buffers (what a WAV part holds; decoder.decode_wav_file path: device scales by 1/32768) ----
+    e2e_pcm16 = None
+    if not args.no_e2e and e2e and e2e.get("value"):
+        try:
+            del host
+            pcm = torch.empty(batch.numel(), dtype=torch.int16, pin_memory=True)
+            pcm.copy_((batch * 32767.0).clamp_(-32768, 32767).to(torch.int16))
+
+            def step_pcm():
+                eng.psk_demod_raw(d, pcm.data_ptr(), offsets, _lib.FB_S16, 0, out_h.data_ptr(), out_offsets,
+                                  ol_h.data_ptr(), sy_h.data_ptr(), st_h.data_ptr())
+                rc = eng.lib.fb_parse_frames_batch(eng.handle, n_rec, out_h.data_ptr(), oo_p, ol_h.data_ptr(), MAXF,
+                                                   ctypes.addressof(fr_h), nf_h.ctypes.data, pb_h.ctypes.data, 0)
+                _lib.check(eng.lib, eng.handle, rc, "fb_parse_frames_batch")
+            step_pcm()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                step_pcm()
+            barrier()
+            s_pcm = (time.perf_counter() - t0) / args.e2e_steps
+            e2e_pcm16 = {"value": n_rec * n_samp / s_pcm / 1e6, "unit": "Msamples/s (this rank)", "ms_per_step": s_pcm * 1e3,
+                         "h2d_bytes_per_step": int(batch.numel() * 2), "payload_bytes_valid": int(pb_h.sum()),
+                         "note": "same recordings quantised to PCM16 as in a WAV part; not the headline e2e (that one moves float32)"}
+            del pcm
+        except RuntimeError as e:
+            e2e_pcm16 = {"value": None, "error": str(e)[:200]}
+
+    # ---- other schemes' dominant kernels on the same device-resident batch (rank 0, informational) -------------------
+    schemes = None
+    if rank == 0 and not args.no_schemes:
+        schemes = scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -355,7 +449,15 @@ def main():
                 "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "note": "fp32-FMA co-limited: ~46 FMA per sample (DESIGN.md); traffic from profiles/ ncu capture"}
+                "note": "fp32-FMA co-limited, not HBM-bound: 32 (FIR, FFMA2) + 8 (slow-pole features) + ~8 FMA per sample, "
+                        "so >= 6.1 ms at the measured 124 FMA/clk/SM (DESIGN.md 4); traffic = ncu dram bytes of the same "
+                        "kernel per launch, scaled from the 32-recording capture in profiles/"}
+    try:      # dram__bytes_read+write per sample from the committed ncu capture (profiles/r01_psk_main_v5c_ncu.txt)
+        for ln in open(os.path.join(ROOT, "profiles", "r01_psk_main_v5c_ncu.txt")):
+            if ln.startswith("dram_bytes_per_sample"):
+                roofline["traffic"] = float(ln.split()[1]) * n_rec * n_samp
+    except Exception:      # noqa: BLE001
+        pass
     cb = None if args.no_cpu else cpu_baseline(30)
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -363,7 +465,8 @@ def main():
             "raw_MB_per_s": raw_all / (ms_per_step * 1e-3) / 1e6, "payload_MB_per_s": payload_all / (ms_per_step * 1e-3) / 1e6,
             "payload_bytes_valid": payload_all, "payload_bytes_sent_rank0": payload_bytes_in,
             "gsamples_per_s_per_gpu": value / 1e3 / world, "gpu_launches": int(launches), "clocks": clk,
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cb,
+            "e2e_pcm16": e2e_pcm16, "schemes": schemes}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
