@@ -8,9 +8,10 @@
 //                    samples (coalesced) and the correlations are reduced with warp shuffles.  Decisions go to
 //                    shared memory, are packed 32 bits per thread and stored big-endian straight into the output
 //                    slot (PSK / OFDM / FSK-HS have no sync search: bytes are the bit stream truncated to x8).
-//   uart_deframe_kernel   B.2's start/8 data LSB-first/stop deframer: inherently sequential, one thread per recording.
+//   uart_*_kernel    B.2's start / 8 data LSB-first / stop deframer, chunk-parallel (speculate, chain, emit).
 //   Goertzel: power = s1^2 + s2^2 - coeff s1 s2 == |sum x[k] e^{-jwk}|^2, evaluated as that correlation in float64.
 #include "common.cuh"
+#include "zp_iir.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -319,29 +320,98 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
   }
 }
 
-// B.2 UART deframer (pyc src 310-324): one thread per recording, bits from the workspace word stream
-__global__ void __launch_bounds__(32) uart_deframe_kernel(const RecPlan* plans, int n_rec, const uint32_t* bits, uint8_t* out,
-                                                           uint64_t* out_len) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rec) return;
-  const RecPlan pl = plans[r];
-  const uint32_t* w = bits + pl.word_off;
-  const int64_t n = pl.nsym;
-  uint8_t* o = out + pl.out_off;
-  uint64_t cnt = 0;
-  auto bit = [&](int64_t i) -> uint32_t { return (__byte_perm(w[i >> 5], 0, 0x0123) >> (31 - (i & 31))) & 1u; };
-  int64_t i = 0;
-  while (i + 10 <= n) {
-    if (bit(i) != 0) { ++i; continue; }
-    if (bit(i + 9) != 1) { ++i; continue; }
-    uint32_t b = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) b |= bit(i + 1 + k) << k;                  // LSB first
-    if (cnt < pl.out_cap) o[cnt] = (uint8_t)b;
+// B.2 UART deframer (pyc src 310-324):  i = 0; while i + 10 <= n: start bit 0 at i and stop bit 1 at i+9 -> emit the 8
+// data bits LSB-first, i += 10; else i += 1.  The walk is a deterministic map next(i) in {i+1, i+10}, so it enters every
+// chunk of UART_L bit positions at one of only 10 offsets.  Three kernels:
+//   uart_spec_kernel   per chunk and per entry offset e < 10: walk the chunk, record (exit offset into the next chunk,
+//                      bytes emitted) -- 10 speculative walks per chunk, all chunks of all recordings in parallel
+//   uart_chain_kernel  per recording: follow the real entry through the chunk table (a short serial loop over a few
+//                      thousand table rows staged through shared memory) -> true entry and output offset of every chunk
+//   uart_emit_kernel   per chunk: walk again from the true entry and store the bytes at their final positions
+#define UART_L 1024
+struct UartRow { uint16_t v[10]; };          // per entry offset: exit offset (4 bits) << 12 | bytes emitted (<= 103)
+
+__device__ __forceinline__ uint32_t uart_bit(const uint32_t* w, int64_t i) {
+  return (__byte_perm(__ldg(&w[i >> 5]), 0, 0x0123) >> (31 - (int)(i & 31))) & 1u;
+}
+
+// walk positions [pos, end) of one recording; EMIT: store bytes at o[cnt...].  Returns the first position >= end (or the
+// position where i + 10 > n stopped the walk) and the byte count.
+template <bool EMIT>
+__device__ __forceinline__ void uart_walk(const uint32_t* w, int64_t n, int64_t pos, int64_t end, uint8_t* o, uint64_t o_pos, uint64_t cap,
+                                          int64_t& pos_out, uint32_t& cnt_out) {
+  uint32_t cnt = 0;
+  int64_t i = pos;
+  while (i < end && i + 10 <= n) {
+    // 10 bits starting at i from at most two words
+    const int64_t wi = i >> 5;
+    const int sh = (int)(i & 31);
+    const uint64_t two = ((uint64_t)__byte_perm(__ldg(&w[wi]), 0, 0x0123) << 32) | __byte_perm(__ldg(&w[wi + 1]), 0, 0x0123);   // 2 spare words per recording
+    const uint32_t ten = (uint32_t)(two >> (54 - sh)) & 0x3ffu;      // bit i is the MSB (bit 9)
+    if ((ten & 0x200u) != 0u || (ten & 1u) == 0u) { ++i; continue; } // start bit must be 0, stop bit 1
+    if (EMIT) {
+      const uint32_t data = (ten >> 1) & 0xffu;                       // bits i+1 .. i+8, first received = LSB
+      if (o_pos + cnt < cap) o[o_pos + cnt] = (uint8_t)(__brev(data) >> 24);
+    }
     ++cnt;
     i += 10;
   }
-  out_len[r] = min(cnt, pl.out_cap);
+  pos_out = i; cnt_out = cnt;
+}
+
+__global__ void __launch_bounds__(256) uart_spec_kernel(const RecPlan* plans, const uint64_t* row_off, const uint32_t* bits, UartRow* rows) {
+  const RecPlan pl = plans[blockIdx.y];
+  const int64_t n = pl.nsym;
+  const int64_t nch = (n + UART_L - 1) / UART_L;
+  const int64_t c = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int e = threadIdx.x & 15;
+  if (c >= nch || e >= 10) return;
+  int64_t pos; uint32_t cnt;
+  uart_walk<false>(bits + pl.word_off, n, c * UART_L + e, (c + 1) * UART_L, nullptr, 0, 0, pos, cnt);
+  const int64_t ex = pos - (c + 1) * UART_L;                          // 0..9, or negative when the walk ended inside the chunk
+  rows[row_off[blockIdx.y] + c].v[e] = (uint16_t)(((ex < 0 ? 15 : (int)ex) << 12) | (cnt & 0xfffu));
+}
+
+__global__ void __launch_bounds__(32) uart_chain_kernel(const RecPlan* plans, const uint64_t* row_off, const UartRow* rows, uint8_t* ent,
+                                                         uint32_t* ooff, uint64_t* out_len) {
+  __shared__ UartRow tile[32];
+  const int r = blockIdx.x, lane = threadIdx.x;
+  const RecPlan pl = plans[r];
+  const int64_t n = pl.nsym;
+  const int64_t nch = (n + UART_L - 1) / UART_L;
+  const UartRow* rr = rows + row_off[r];
+  int e = 0;
+  uint32_t base = 0;
+  for (int64_t c0 = 0; c0 < nch; c0 += 32) {
+    if (c0 + lane < nch) tile[lane] = rr[c0 + lane];
+    __syncwarp();
+    if (lane == 0) {
+      for (int k = 0; k < 32 && c0 + k < nch; ++k) {
+        ent[row_off[r] + c0 + k] = (uint8_t)e;
+        ooff[row_off[r] + c0 + k] = base;
+        if (e < 10) {
+          const uint16_t v = tile[k].v[e];
+          base += v & 0xfffu;
+          e = v >> 12;                                                // 15: the walk has ended, later chunks emit nothing
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) out_len[r] = min((uint64_t)base, pl.out_cap);
+}
+
+__global__ void __launch_bounds__(256) uart_emit_kernel(const RecPlan* plans, const uint64_t* row_off, const uint32_t* bits, const uint8_t* ent,
+                                                         const uint32_t* ooff, uint8_t* out) {
+  const RecPlan pl = plans[blockIdx.y];
+  const int64_t n = pl.nsym;
+  const int64_t nch = (n + UART_L - 1) / UART_L;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nch) return;
+  const int e = ent[row_off[blockIdx.y] + c];
+  if (e >= 10) return;
+  int64_t pos; uint32_t cnt;
+  uart_walk<true>(bits + pl.word_off, n, c * UART_L + e, (c + 1) * UART_L, out + pl.out_off, ooff[row_off[blockIdx.y] + c], pl.out_cap, pos, cnt);
 }
 
 __global__ void __launch_bounds__(FB_THREADS) v1_finish_kernel(const RecPlan* plans, int n_rec, int bpsym, uint64_t* out_len, int32_t* status,
@@ -353,86 +423,9 @@ __global__ void __launch_bounds__(FB_THREADS) v1_finish_kernel(const RecPlan* pl
 }
 
 // ------------------------------------------------------------------------------------------------ pre-filter (B.1)
-// scipy filtfilt (order <= 8, float64), chunk-parallel exactly like fsk_v2.cu; output cast to float32 (B.2: the v1 code
+// scipy filtfilt (Butterworth-4 band-pass: 8th order, float64), zp_iir.cuh; output cast to float32 (B.2: the v1 code
 // re-casts the filtered record to float32 before the Goertzel loop).
 #define PF_ORD 8
-#define PF_CHUNK 1024
-struct PfFilt { double b[PF_ORD + 1], a[PF_ORD + 1], zi[PF_ORD]; int32_t w, pad; };
-
-template <typename TIn>
-__device__ __forceinline__ double pf_x_ext(const void* samples, uint64_t off, int64_t N, int64_t n) {
-  if (n < 0) return 2.0 * load_sample_d<TIn>(samples, off) - load_sample_d<TIn>(samples, off + (uint64_t)(-n));
-  if (n > N - 1)
-    return 2.0 * load_sample_d<TIn>(samples, off + (uint64_t)(N - 1)) - load_sample_d<TIn>(samples, off + (uint64_t)(2 * (N - 1) - n));
-  return load_sample_d<TIn>(samples, off + (uint64_t)n);
-}
-
-template <typename TIn>
-// grid.y = recording of the group (all recordings of a group run in ONE launch: a single 3-minute recording is only
-// ~17 k chunk-threads, far too few to fill 148 SMs); yoff[r] = first double of recording r's forward-pass scratch
-__global__ void __launch_bounds__(64) pf_fwd_kernel(const void* samples, const RecPlan* plans, const uint64_t* yoff, PfFilt t, double* ybase) {
-  const RecPlan pl = plans[blockIdx.y];
-  if (pl.status != FB_ST_OK) return;
-  const uint64_t off = pl.off;
-  const int64_t N = (int64_t)pl.n;
-  double* yfwd = ybase + yoff[blockIdx.y];
-  const int64_t Next = N + 2 * t.pad;
-  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PF_CHUNK;
-  if (c0 >= Next) return;
-  const int64_t c1 = min(Next, c0 + PF_CHUNK), s = max((int64_t)0, c0 - t.w);
-  double z[PF_ORD];
-  const double x0 = pf_x_ext<TIn>(samples, off, N, s - t.pad);
-#pragma unroll
-  for (int i = 0; i < PF_ORD; ++i) z[i] = (s == 0) ? t.zi[i] * x0 : 0.0;
-  constexpr int EB = 16;
-  for (int64_t e0 = s; e0 < c1; e0 += EB) {
-    double xb[EB];
-#pragma unroll
-    for (int u = 0; u < EB; ++u) xb[u] = (e0 + u < c1) ? pf_x_ext<TIn>(samples, off, N, e0 + u - t.pad) : 0.0;
-#pragma unroll
-    for (int u = 0; u < EB; ++u) {
-      const double xv = xb[u], y = t.b[0] * xv + z[0];
-#pragma unroll
-      for (int k = 0; k < PF_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
-      z[PF_ORD - 1] = t.b[PF_ORD] * xv - t.a[PF_ORD] * y;
-      if (e0 + u >= c0 && e0 + u < c1) yfwd[e0 + u] = y;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(64) pf_bwd_kernel(const double* ybase, const RecPlan* plans, const uint64_t* yoff, PfFilt t, float* fbase) {
-  const RecPlan pl = plans[blockIdx.y];
-  if (pl.status != FB_ST_OK) return;
-  const int64_t N = (int64_t)pl.n;
-  const double* yfwd = ybase + yoff[blockIdx.y];
-  float* f32 = fbase + pl.off;
-  const int64_t Next = N + 2 * t.pad;
-  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PF_CHUNK;
-  if (c0 >= Next) return;
-  const int64_t c1 = min(Next, c0 + PF_CHUNK), s = min(Next - 1, c1 - 1 + t.w);
-  double z[PF_ORD];
-  const double y0 = yfwd[s];
-#pragma unroll
-  for (int i = 0; i < PF_ORD; ++i) z[i] = (s == Next - 1) ? t.zi[i] * y0 : 0.0;
-  constexpr int EB = 16;
-  for (int64_t e0 = s; e0 >= c0; e0 -= EB) {
-    double xb[EB];
-#pragma unroll
-    for (int u = 0; u < EB; ++u) xb[u] = (e0 - u >= c0) ? yfwd[e0 - u] : 0.0;
-#pragma unroll
-    for (int u = 0; u < EB; ++u) {
-      const int64_t e = e0 - u;
-      if (e >= c0) {
-        const double xv = xb[u], y = t.b[0] * xv + z[0];
-#pragma unroll
-        for (int k = 0; k < PF_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
-        z[PF_ORD - 1] = t.b[PF_ORD] * xv - t.a[PF_ORD] * y;
-        const int64_t n = e - t.pad;
-        if (e < c1 && n >= 0 && n < N) f32[n] = (float)y;
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ host side
 extern "C" uint64_t fb_v1_out_bound(const fb_v1_params* p, uint64_t n_samples) {
@@ -543,45 +536,48 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   int kdtype = dtype;
   if (p.prefilter) {
     // filtered copy of the whole batch as float32 (B.2 casts the filtered record back to float32): scratch = [f32 batch]
-    // [yfwd of one group of recordings][yoff table].  Recordings are filtered in groups of up to ~4 GB of float64
-    // forward-pass scratch, every group in two launches (forward chunks, backward chunks).
-    const size_t o_y = ((size_t)total_samples * 4 + 255) / 256 * 256;
-    const uint64_t group_doubles = std::max<uint64_t>((uint64_t)maxN + 2 * p.bp_pad + 16, (uint64_t)1 << 29);
-    const size_t o_t = o_y + ((size_t)std::min<uint64_t>(group_doubles, (uint64_t)total_samples + (uint64_t)n_rec * (2 * p.bp_pad + 16)) * 8 + 255) / 256 * 256;
-    if ((rc = fb_ensure(h, h->scratch, o_t + (size_t)n_rec * 8 + 16))) return rc;
-    float* f32 = (float*)h->scratch.p;
-    double* yfwd = (double*)((char*)h->scratch.p + o_y);
-    uint64_t* d_yoff = (uint64_t*)((char*)h->scratch.p + o_t);
-    PfFilt t;
-    for (int i = 0; i <= PF_ORD; ++i) { t.b[i] = p.bp_b[i]; t.a[i] = p.bp_a[i]; }
-    for (int i = 0; i < PF_ORD; ++i) t.zi[i] = p.bp_zi[i];
-    t.w = p.bp_w; t.pad = p.bp_pad;
-    std::vector<uint64_t> yoff(n_rec, 0);
+    // [transposed forward scratch of one group of recordings][ZpRec table].  Recordings are filtered in groups of up to
+    // ~4 GB of float64 scratch, every group in two launches (forward chunks, backward chunks; grid.y = recording).
+    const int L = zp_chunk_len(p.bp_w), W16 = (std::min(p.bp_w, L) + 15) / 16 * 16;
+    std::vector<ZpRec> zr(n_rec);
     std::vector<std::pair<int, int>> groups;               // [first, last) recordings per launch group
+    const uint64_t group_doubles = (uint64_t)1 << 29;
+    uint64_t max_used = 0;
     for (int r0 = 0; r0 < n_rec;) {
       uint64_t used = 0;
       int r1 = r0;
       while (r1 < n_rec && r1 - r0 < 65535) {
-        const uint64_t need = plans[r1].n + 2 * (uint64_t)p.bp_pad + 16;
+        ZpRec& q = zr[r1];
+        q.off = plans[r1].off; q.out_off = plans[r1].off;
+        q.N = plans[r1].status == FB_ST_OK ? (int64_t)plans[r1].n : 0;
+        q.nch = q.N > 0 ? (q.N + 2 * p.bp_pad + L - 1) / L : 0;
+        const uint64_t need = (uint64_t)q.nch * L;
         if (r1 > r0 && used + need > group_doubles) break;
-        yoff[r1] = used; used += need; ++r1;
+        q.y_off = used; used += need; ++r1;
       }
+      max_used = std::max(max_used, used);
       groups.emplace_back(r0, r1);
       r0 = r1;
     }
-    FB_CUDA(h, cudaMemcpyAsync(d_yoff, yoff.data(), (size_t)n_rec * 8, cudaMemcpyHostToDevice, h->stream));
+    const size_t o_y = ((size_t)total_samples * 4 + 255) / 256 * 256, o_t = o_y + ((size_t)max_used * 8 + 255) / 256 * 256;
+    if ((rc = fb_ensure(h, h->scratch, o_t + (size_t)n_rec * sizeof(ZpRec) + 16))) return rc;
+    float* f32 = (float*)h->scratch.p;
+    double* yfwd = (double*)((char*)h->scratch.p + o_y);
+    ZpRec* d_zr = (ZpRec*)((char*)h->scratch.p + o_t);
+    ZpFilt<PF_ORD> t;
+    for (int i = 0; i <= PF_ORD; ++i) { t.b[i] = p.bp_b[i]; t.a[i] = p.bp_a[i]; }
+    for (int i = 0; i < PF_ORD; ++i) t.zi[i] = p.bp_zi[i];
+    t.w = p.bp_w; t.pad = p.bp_pad;
+    FB_CUDA(h, cudaMemcpyAsync(d_zr, zr.data(), (size_t)n_rec * sizeof(ZpRec), cudaMemcpyHostToDevice, h->stream));
     for (auto& gr : groups) {
       int64_t gmax = 0;
-      for (int r = gr.first; r < gr.second; ++r) if (plans[r].status == FB_ST_OK) gmax = std::max<int64_t>(gmax, (int64_t)plans[r].n);
+      for (int r = gr.first; r < gr.second; ++r) gmax = std::max<int64_t>(gmax, zr[r].nch);
       if (gmax == 0) continue;
-      const int64_t Next = gmax + 2 * p.bp_pad;
-      const int nthreads = (int)((Next + PF_CHUNK - 1) / PF_CHUNK);
-      const dim3 grid((nthreads + 63) / 64, gr.second - gr.first);
-      const RecPlan* gp = (const RecPlan*)h->plans.p + gr.first;
-      if (dtype == FB_F32) pf_fwd_kernel<float><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
-      else if (dtype == FB_F64) pf_fwd_kernel<double><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
-      else pf_fwd_kernel<int16_t><<<grid, 64, 0, h->stream>>>(d_samples, gp, d_yoff + gr.first, t, yfwd);
-      pf_bwd_kernel<<<grid, 64, 0, h->stream>>>(yfwd, gp, d_yoff + gr.first, t, f32);
+      const dim3 grid((unsigned)((gmax + ZP_THREADS - 1) / ZP_THREADS), gr.second - gr.first);
+      if (dtype == FB_F32) zp_fwd_kernel<float, PF_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, L, W16, yfwd);
+      else if (dtype == FB_F64) zp_fwd_kernel<double, PF_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, L, W16, yfwd);
+      else zp_fwd_kernel<int16_t, PF_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, L, W16, yfwd);
+      zp_bwd_kernel<float, PF_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(yfwd, d_zr + gr.first, t, L, W16, f32);
       h->launches += 2;
     }
     d_samples = f32;
@@ -621,8 +617,30 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
     h->launches++;
   }
   if (p.uart) {
-    uart_deframe_kernel<<<(n_rec + 31) / 32, 32, 0, h->stream>>>((const RecPlan*)h->plans.p, n_rec, (const uint32_t*)h->bits.p, d_out, d_out_len);
-    h->launches++;
+    // chunk tables: [row_off (n_rec u64)][rows][ent][ooff]
+    std::vector<uint64_t> row_off(n_rec + 1, 0);
+    int64_t max_ch = 1;
+    for (int r = 0; r < n_rec; ++r) {
+      const int64_t nch = ((int64_t)plans[r].nsym + UART_L - 1) / UART_L;
+      row_off[r + 1] = row_off[r] + (uint64_t)nch;
+      max_ch = std::max(max_ch, nch);
+    }
+    const size_t o_rows = ((size_t)(n_rec + 1) * 8 + 255) / 256 * 256, o_ent = o_rows + ((size_t)row_off[n_rec] * sizeof(UartRow) + 255) / 256 * 256,
+                 o_oo = o_ent + ((size_t)row_off[n_rec] + 255) / 256 * 256, tot = o_oo + (size_t)row_off[n_rec] * 4 + 16;
+    if ((rc = fb_ensure(h, h->misc, tot))) return rc;
+    char* ws = (char*)h->misc.p;
+    FB_CUDA(h, cudaMemcpyAsync(ws, row_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    const RecPlan* dp = (const RecPlan*)h->plans.p;
+    const uint32_t* db = (const uint32_t*)h->bits.p;
+    for (int r0 = 0; r0 < n_rec; r0 += 65535) {
+      const int nr = std::min(65535, n_rec - r0);
+      uart_spec_kernel<<<dim3((unsigned)((max_ch + 15) / 16), nr), 256, 0, h->stream>>>(dp + r0, (const uint64_t*)ws + r0, db, (UartRow*)(ws + o_rows));
+      uart_chain_kernel<<<nr, 32, 0, h->stream>>>(dp + r0, (const uint64_t*)ws + r0, (const UartRow*)(ws + o_rows), (uint8_t*)(ws + o_ent),
+                                                  (uint32_t*)(ws + o_oo), d_out_len + r0);
+      uart_emit_kernel<<<dim3((unsigned)((max_ch + 255) / 256), nr), 256, 0, h->stream>>>(dp + r0, (const uint64_t*)ws + r0, db,
+                                                                                          (const uint8_t*)(ws + o_ent), (const uint32_t*)(ws + o_oo), d_out);
+      h->launches += 3;
+    }
   }
   v1_finish_kernel<<<(n_rec + FB_THREADS - 1) / FB_THREADS, FB_THREADS, 0, h->stream>>>((const RecPlan*)h->plans.p, n_rec, p.bits_per_sym,
                                                                                       d_out_len, d_status, p.uart ? 0 : 1);
