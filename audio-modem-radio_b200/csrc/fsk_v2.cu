@@ -1,10 +1,9 @@
 // v2 FSK receive chain on sm_100a: replaces fsk_demodulate (modem.py:298-341) for valid tone sets.
 //
 // Per tone (modem.py:306-309):  f = filtfilt(butter(3, [f-b, f+b]), x);  env = |hilbert(f)|
-//   iir_fwd_kernel / iir_bwd_kernel   scipy.signal.filtfilt in float64: odd extension by padlen, lfilter_zi start-up,
-//                                     DF2T forward then backward.  Chunk-parallel: one thread per chunk of the
-//                                     extended record, exact state at the true ends, zero state + `w` warm-up samples
-//                                     (pole decay to 1e-12) at interior cuts.
+//   zp_fwd_kernel / zp_bwd_kernel (zp_iir.cuh)   scipy.signal.filtfilt in float64: odd extension by padlen, lfilter_zi
+//                                     start-up, DF2T forward then backward.  Chunk-parallel with coalesced traffic; all
+//                                     recordings of a group in one launch per pass.
 //   cuFFT D2Z -> analytic_fill -> cuFFT Z2Z inverse   scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and
 //                                     one length-N inverse FFT over the whole recording (circular); the library FFT is
 //                                     used for this one library-shaped op exactly as the reference uses pocketfft.
@@ -12,87 +11,13 @@
 // (window truncated at the record end; spb < 4 -> empty window -> no bits).  fsk_vote_kernel packs the decided bits
 // into the same big-endian word stream the DPSK kernels write; backend.cu does the magic search and byte packing.
 #include "common.cuh"
+#include "zp_iir.cuh"
 
 #include <cufft.h>
 #include <algorithm>
 #include <map>
 
 #define FSK_ORD 6            // butter(3, band) -> 6th order, 7 coefficients
-#define FSK_CHUNK 2048
-
-struct FskTone {
-  double b[FSK_ORD + 1], a[FSK_ORD + 1], zi[FSK_ORD];
-  int32_t w, pad;
-};
-
-template <typename TIn>
-__device__ __forceinline__ double fsk_x_ext(const void* samples, uint64_t off, int64_t N, int64_t n) {
-  if (n < 0) return 2.0 * load_sample_d<TIn>(samples, off) - load_sample_d<TIn>(samples, off + (uint64_t)(-n));
-  if (n > N - 1)
-    return 2.0 * load_sample_d<TIn>(samples, off + (uint64_t)(N - 1)) - load_sample_d<TIn>(samples, off + (uint64_t)(2 * (N - 1) - n));
-  return load_sample_d<TIn>(samples, off + (uint64_t)n);
-}
-
-// forward pass over the extended record e in [0, Next), ext[e] = x_ext(e - pad); writes yfwd[e]
-template <typename TIn>
-__global__ void __launch_bounds__(64) iir_fwd_kernel(const void* samples, uint64_t off, int64_t N, FskTone t, double* yfwd) {
-  const int64_t Next = N + 2 * t.pad;
-  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * FSK_CHUNK;
-  if (c0 >= Next) return;
-  const int64_t c1 = min(Next, c0 + FSK_CHUNK);
-  const int64_t s = max((int64_t)0, c0 - t.w);
-  double z[FSK_ORD];
-  const double x0 = fsk_x_ext<TIn>(samples, off, N, s - t.pad);
-#pragma unroll
-  for (int i = 0; i < FSK_ORD; ++i) z[i] = (s == 0) ? t.zi[i] * x0 : 0.0;
-  constexpr int EB = 16;
-  for (int64_t e0 = s; e0 < c1; e0 += EB) {
-    double xb[EB];
-#pragma unroll
-    for (int u = 0; u < EB; ++u) xb[u] = (e0 + u < c1) ? fsk_x_ext<TIn>(samples, off, N, e0 + u - t.pad) : 0.0;
-#pragma unroll
-    for (int u = 0; u < EB; ++u) {
-      const double xv = xb[u];
-      const double y = t.b[0] * xv + z[0];
-#pragma unroll
-      for (int k = 0; k < FSK_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
-      z[FSK_ORD - 1] = t.b[FSK_ORD] * xv - t.a[FSK_ORD] * y;
-      if (e0 + u >= c0 && e0 + u < c1) yfwd[e0 + u] = y;
-    }
-  }
-}
-
-// backward pass over yfwd; writes f[n] for the un-extended record
-__global__ void __launch_bounds__(64) iir_bwd_kernel(const double* yfwd, int64_t N, FskTone t, double* f) {
-  const int64_t Next = N + 2 * t.pad;
-  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * FSK_CHUNK;
-  if (c0 >= Next) return;
-  const int64_t c1 = min(Next, c0 + FSK_CHUNK);
-  const int64_t s = min(Next - 1, c1 - 1 + t.w);           // first (highest) index processed
-  double z[FSK_ORD];
-  const double y0 = yfwd[s];
-#pragma unroll
-  for (int i = 0; i < FSK_ORD; ++i) z[i] = (s == Next - 1) ? t.zi[i] * y0 : 0.0;
-  constexpr int EB = 16;
-  for (int64_t e0 = s; e0 >= c0; e0 -= EB) {
-    double xb[EB];
-#pragma unroll
-    for (int u = 0; u < EB; ++u) xb[u] = (e0 - u >= c0) ? yfwd[e0 - u] : 0.0;
-#pragma unroll
-    for (int u = 0; u < EB; ++u) {
-      const int64_t e = e0 - u;
-      if (e >= c0) {
-        const double xv = xb[u];
-        const double y = t.b[0] * xv + z[0];
-#pragma unroll
-        for (int k = 0; k < FSK_ORD - 1; ++k) z[k] = t.b[k + 1] * xv + z[k + 1] - t.a[k + 1] * y;
-        z[FSK_ORD - 1] = t.b[FSK_ORD] * xv - t.a[FSK_ORD] * y;
-        const int64_t n = e - t.pad;
-        if (e < c1 && n >= 0 && n < N) f[n] = y;
-      }
-    }
-  }
-}
 
 // scipy.signal.hilbert's one-sided mask: h[0] = 1, h[1 .. ceil(N/2)-1] = 2, h[N/2] = 1 (N even), 0 above
 __global__ void __launch_bounds__(FB_THREADS) analytic_fill_kernel(const cufftDoubleComplex* X, cufftDoubleComplex* Z, int64_t N) {
@@ -150,26 +75,16 @@ void fb_fsk_release(fb_handle* h) {
   g_fsk_plans.erase(it);
 }
 
-template <typename TIn>
-static int fsk_one(fb_handle* h, const fb_fsk_design& d, const void* d_samples, uint64_t off, int64_t N, int64_t nbits,
-                   uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2z, double* yfwd, double* f,
-                   cufftDoubleComplex* X, cufftDoubleComplex* Z, double* env, uint8_t* cmp) {
+// Hilbert envelope compare + vote for one recording whose two tone-filtered copies f0, f1 (float64) are ready
+static int fsk_one(fb_handle* h, const fb_fsk_design& d, int64_t N, int64_t nbits, uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2z,
+                   double* f0, double* f1, cufftDoubleComplex* X, cufftDoubleComplex* Z, double* env, uint8_t* cmp) {
   for (int tone = 0; tone < 2; ++tone) {
-    FskTone t;
-    for (int i = 0; i <= FSK_ORD; ++i) { t.b[i] = d.b[tone][i]; t.a[i] = d.a[tone][i]; }
-    for (int i = 0; i < FSK_ORD; ++i) t.zi[i] = d.zi[tone][i];
-    t.w = d.w[tone]; t.pad = d.pad;
-    const int64_t Next = N + 2 * d.pad;
-    const int nthreads = (int)((Next + FSK_CHUNK - 1) / FSK_CHUNK);
-    const int nblocks = (nthreads + 63) / 64;
-    iir_fwd_kernel<TIn><<<nblocks, 64, 0, h->stream>>>(d_samples, off, N, t, yfwd);
-    iir_bwd_kernel<<<nblocks, 64, 0, h->stream>>>(yfwd, N, t, f);
-    if (cufftExecD2Z(p_d2z, f, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
+    if (cufftExecD2Z(p_d2z, tone ? f1 : f0, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
     const int g = (int)std::min<int64_t>(148 * 8, (N + FB_THREADS - 1) / FB_THREADS);
     analytic_fill_kernel<<<g, FB_THREADS, 0, h->stream>>>(X, Z, N);
     if (cufftExecZ2Z(p_z2z, Z, Z, CUFFT_INVERSE) != CUFFT_SUCCESS) { h->err = "cufftExecZ2Z failed"; return FB_ECUDA; }
     env_kernel<<<g, FB_THREADS, 0, h->stream>>>(Z, N, env, cmp, tone);
-    h->launches += 4;
+    h->launches += 2;
   }
   if (nbits > 0) {
     const int g = (int)std::min<int64_t>(148 * 8, ((nbits + 31) / 32 + FB_THREADS - 1) / FB_THREADS);
@@ -233,41 +148,88 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
   if ((rc = fb_ensure(h, h->bits, (size_t)(words + 4) * 4))) return rc;
   if ((rc = fb_ensure(h, h->plans, (size_t)n_rec * sizeof(RecPlan)))) return rc;
   FB_CUDA(h, cudaMemcpyAsync(h->plans.p, plans.data(), (size_t)n_rec * sizeof(RecPlan), cudaMemcpyHostToDevice, h->stream));
-  // scratch for the longest recording: yfwd | f | X | Z | env | cmp
-  const size_t nE = (size_t)maxN + 2 * d.pad + 16, nN = (size_t)maxN + 16;
+  // scratch: [X | Z | env | cmp for the longest recording][f0 | f1 | transposed forward scratch for one GROUP of recordings]
+  // [ZpRec table].  The two tone filters run for a whole group per launch (grid.y = recording); the Hilbert step then
+  // goes recording by recording (one library FFT each).
+  const size_t nN = (size_t)maxN + 16;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };            // cuFFT wants 16-byte aligned complex buffers
-  const size_t o_f = al(nE * 8), o_X = al(o_f + nN * 8), o_Z = al(o_X + (nN / 2 + 2) * 16), o_env = al(o_Z + nN * 16), o_cmp = al(o_env + nN * 8);
+  const size_t o_Z = al((nN / 2 + 2) * 16), o_env = al(o_Z + nN * 16), o_cmp = al(o_env + nN * 8), o_grp = al(o_cmp + nN + 64);
+  const int Lc = zp_chunk_len(std::max(d.w[0], d.w[1]));
+  std::vector<ZpRec> zr(n_rec);
+  std::vector<uint64_t> f_off(n_rec, 0);
+  std::vector<std::pair<int, int>> groups;
+  const uint64_t group_doubles = (uint64_t)1 << 28;                    // 2 GB of transposed scratch per group
+  uint64_t max_y = 0, max_f = 0;
+  for (int r0 = 0; r0 < n_rec;) {
+    uint64_t used = 0, fused = 0;
+    int r1 = r0;
+    while (r1 < n_rec && r1 - r0 < 65535) {
+      ZpRec& q = zr[r1];
+      q.off = plans[r1].off;
+      q.N = plans[r1].status == FB_ST_OK ? (int64_t)plans[r1].n : 0;
+      q.nch = q.N > 0 ? (q.N + 2 * d.pad + Lc - 1) / Lc : 0;
+      const uint64_t need = (uint64_t)q.nch * Lc;
+      if (r1 > r0 && used + need > group_doubles) break;
+      q.y_off = used; used += need;
+      q.out_off = fused; f_off[r1] = fused; fused += ((uint64_t)q.N + 31) / 32 * 32;
+      ++r1;
+    }
+    max_y = std::max(max_y, used); max_f = std::max(max_f, fused);
+    groups.emplace_back(r0, r1);
+    r0 = r1;
+  }
+  const size_t o_f1 = o_grp + al((size_t)max_f * 8), o_y = o_f1 + al((size_t)max_f * 8), o_t = o_y + al((size_t)max_y * 8);
   if (maxN > 0) {
-    if ((rc = fb_ensure(h, h->scratch, o_cmp + nN + 64))) return rc;
+    if ((rc = fb_ensure(h, h->scratch, o_t + (size_t)n_rec * sizeof(ZpRec) + 64))) return rc;
   }
   char* sc = (char*)h->scratch.p;
   FskPlans& fp = g_fsk_plans[h];
-  for (int r = 0; r < n_rec; ++r) {
-    const RecPlan& p = plans[r];
-    if (p.status != FB_ST_OK) continue;
-    const int64_t N = (int64_t)p.n;
-    auto it = fp.plans.find(N);
-    if (it == fp.plans.end()) {
-      if (fp.plans.size() >= 8) {                          // bounded plan cache
-        for (auto& q : fp.plans) { cufftDestroy(q.second.first); cufftDestroy(q.second.second); }
-        fp.plans.clear();
+  if (maxN > 0) {
+    ZpRec* d_zr = (ZpRec*)(sc + o_t);
+    FB_CUDA(h, cudaMemcpyAsync(d_zr, zr.data(), (size_t)n_rec * sizeof(ZpRec), cudaMemcpyHostToDevice, h->stream));
+    double* fbuf[2] = {(double*)(sc + o_grp), (double*)(sc + o_f1)};
+    double* ytr = (double*)(sc + o_y);
+    for (auto& gr : groups) {
+      int64_t gmax = 0;
+      for (int r = gr.first; r < gr.second; ++r) gmax = std::max<int64_t>(gmax, zr[r].nch);
+      if (gmax == 0) continue;
+      const dim3 grid((unsigned)((gmax + ZP_THREADS - 1) / ZP_THREADS), gr.second - gr.first);
+      for (int tone = 0; tone < 2; ++tone) {
+        ZpFilt<FSK_ORD> t;
+        for (int i = 0; i <= FSK_ORD; ++i) { t.b[i] = d.b[tone][i]; t.a[i] = d.a[tone][i]; }
+        for (int i = 0; i < FSK_ORD; ++i) t.zi[i] = d.zi[tone][i];
+        t.w = d.w[tone]; t.pad = d.pad;
+        const int W16 = (std::min(d.w[tone], Lc) + 15) / 16 * 16;
+        if (dtype == FB_F32) zp_fwd_kernel<float, FSK_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, Lc, W16, ytr);
+        else if (dtype == FB_F64) zp_fwd_kernel<double, FSK_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, Lc, W16, ytr);
+        else zp_fwd_kernel<int16_t, FSK_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(d_samples, d_zr + gr.first, t, Lc, W16, ytr);
+        zp_bwd_kernel<double, FSK_ORD><<<grid, ZP_THREADS, 0, h->stream>>>(ytr, d_zr + gr.first, t, Lc, W16, fbuf[tone]);
+        h->launches += 2;
       }
-      cufftHandle a, b;
-      if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2Z, 1) != CUFFT_SUCCESS) {
-        h->err = "cufftPlan1d failed";
-        return FB_ECUDA;
+      for (int r = gr.first; r < gr.second; ++r) {
+        const RecPlan& p = plans[r];
+        if (p.status != FB_ST_OK) continue;
+        const int64_t N = (int64_t)p.n;
+        auto it = fp.plans.find(N);
+        if (it == fp.plans.end()) {
+          if (fp.plans.size() >= 8) {                          // bounded plan cache
+            for (auto& q : fp.plans) { cufftDestroy(q.second.first); cufftDestroy(q.second.second); }
+            fp.plans.clear();
+          }
+          cufftHandle a, b;
+          if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2Z, 1) != CUFFT_SUCCESS) {
+            h->err = "cufftPlan1d failed";
+            return FB_ECUDA;
+          }
+          cufftSetStream(a, h->stream); cufftSetStream(b, h->stream);
+          it = fp.plans.emplace(N, std::make_pair(a, b)).first;
+        }
+        uint32_t* d_words = (uint32_t*)h->bits.p + p.word_off;
+        rc = fsk_one(h, d, N, p.ndsym, d_words, it->second.first, it->second.second, fbuf[0] + f_off[r], fbuf[1] + f_off[r],
+                     (cufftDoubleComplex*)sc, (cufftDoubleComplex*)(sc + o_Z), (double*)(sc + o_env), (uint8_t*)(sc + o_cmp));
+        if (rc) return rc;
       }
-      cufftSetStream(a, h->stream); cufftSetStream(b, h->stream);
-      it = fp.plans.emplace(N, std::make_pair(a, b)).first;
     }
-    uint32_t* d_words = (uint32_t*)h->bits.p + p.word_off;
-    double* yfwd = (double*)sc; double* f = (double*)(sc + o_f);
-    cufftDoubleComplex* X = (cufftDoubleComplex*)(sc + o_X); cufftDoubleComplex* Z = (cufftDoubleComplex*)(sc + o_Z);
-    double* env = (double*)(sc + o_env); uint8_t* cmp = (uint8_t*)(sc + o_cmp);
-    if (dtype == FB_F32) rc = fsk_one<float>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
-    else if (dtype == FB_F64) rc = fsk_one<double>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
-    else rc = fsk_one<int16_t>(h, d, d_samples, p.off, N, p.ndsym, d_words, it->second.first, it->second.second, yfwd, f, X, Z, env, cmp);
-    if (rc) return rc;
   }
   rc = fb_bits_backend(h, n_rec, (const RecPlan*)h->plans.p, plans, 1, (const uint32_t*)h->bits.p, d_out, d_out_len, d_sync, d_status);
   if (rc) return rc;
