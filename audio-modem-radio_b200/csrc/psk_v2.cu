@@ -91,6 +91,18 @@ template <> __device__ __forceinline__ float4 load4<int16_t>(const void* base, u
   return make_float4((float)v.x * k, (float)v.y * k, (float)v.z * k, (float)v.w * k);
 }
 
+// two consecutive samples starting at an EVEN element index (8- / 4- / 16-byte aligned), as floats
+template <typename T> __device__ __forceinline__ float2 load_pair(const T* p);
+template <> __device__ __forceinline__ float2 load_pair<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <> __device__ __forceinline__ float2 load_pair<double>(const double* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return make_float2((float)v.x, (float)v.y);
+}
+template <> __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* p) {
+  const short2 v = __ldg(reinterpret_cast<const short2*>(p));
+  return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+}
+
 // packed fp32 pairs (FFMA2 on sm_100a): a complex accumulator is one 64-bit register pair
 __device__ __forceinline__ float2 bfma(float x, float2 w, float2 acc) {       // acc + x * w   (x broadcast)
   return __ffma2_rn(make_float2(x, x), w, acc);
@@ -108,7 +120,7 @@ __device__ __forceinline__ float2 map22(float4 m, float fr, float fi, float2 acc
 // window loads of a quarter warp (8 symbols per thread) hit 8 distinct 16-byte bank groups instead of 4
 __device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2); }
 
-// SPS > 0: samples per symbol known at compile time (even; float32 input): the staging loop is fully unrolled with all
+// SPS > 0: samples per symbol known at compile time (even): the staging loop is fully unrolled with all
 // of a thread's loads in flight before the first store; SPS == 0: runtime sps.
 template <typename TIn, int NT, int SPS>
 __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
@@ -139,12 +151,12 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     const int64_t n_a = (int64_t)a.n0 + (int64_t)ca * sps;          // sample index of staged element 0
     const int ncols = min(P, cc + ns + a.dl + 1);
     bool done = false;
-    if constexpr (SPS > 0 && sizeof(TIn) == 4 && (SPS & 1) == 0) {
-      // 8-byte loads need an even element index: start one sample early when the column start is odd (the parity is
+    if constexpr (SPS > 0 && (SPS & 1) == 0) {
+      // pair loads need an even element index: start one sample early when the column start is odd (the parity is
       // the same for every column).  Loaded element k of column c is X[k - s][c]; k - s == -1 is X[sps-1][c-1].
       const int s = (int)((pl.off + (uint64_t)n_a) & 1);
       if (n_a - s >= 0 && n_a + (int64_t)(ncols + 1) * SPS <= N) {      // whole staged range inside the recording
-        const float* base = reinterpret_cast<const float*>(a.samples) + pl.off + n_a - s;
+        const TIn* base = reinterpret_cast<const TIn*>(a.samples) + pl.off + n_a - s;
         constexpr int KC = 4;
         for (int c0 = tid; c0 < ncols + s; c0 += KC * nthr) {
           constexpr int HS = SPS > 1 ? SPS / 2 : 1;
@@ -153,9 +165,9 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
           for (int k = 0; k < KC; ++k) {
             const int c = c0 + k * nthr;
             if (c < ncols + s) {
-              const float2* src = reinterpret_cast<const float2*>(base + (int64_t)c * SPS);
+              const TIn* src = base + (int64_t)c * SPS;
 #pragma unroll
-              for (int i = 0; i < SPS / 2; ++i) v[k][i] = __ldg(src + i);
+              for (int i = 0; i < SPS / 2; ++i) v[k][i] = load_pair<TIn>(src + 2 * i);
             }
           }
 #pragma unroll
@@ -759,7 +771,7 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
       FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       psk_main_kernel<TIn, NTV, SPSV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
     } while (0)
-    if (ntv == 16 && ma.sps == 10 && sizeof(TIn) == 4) FB_LAUNCH_MAIN(16, 10);      // 9600 sym/s at 96 kHz, float32 samples
+    if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10);                          // 9600 sym/s at 96 kHz
     else if (ntv == 14) FB_LAUNCH_MAIN(14, 0);
     else if (ntv == 16) FB_LAUNCH_MAIN(16, 0);
     else if (ntv == 18) FB_LAUNCH_MAIN(18, 0);
