@@ -236,6 +236,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-schemes", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, torchrun) also write to fd 1, so keep the
+    # real stdout aside for the result line and send everything else to stderr
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,7 +269,8 @@ def main():
                           "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              file=result_out, flush=True)
         return
 
     import torch
@@ -476,7 +482,7 @@ def main():
             "gsamples_per_s_per_gpu": value / 1e3 / world, "gpu_launches": int(launches), "clocks": clk,
             "e2e": (e2e_pcm16 if (e2e_pcm16 and e2e_pcm16.get("value")) else e2e), "roofline": roofline, "cpu_baseline": cb,
             "e2e_f32": e2e, "schemes": schemes}
-    print(json.dumps(line))
+    print(json.dumps(line), file=result_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
