@@ -62,6 +62,8 @@ extern "C" fb_handle* fb_create(int device) {
     return nullptr;
   }
   fb_handle* h = new fb_handle();
+  for (auto& e : h->ev_copy)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete h; return nullptr; }
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   // stream2 carries the small latency-bound edge kernels that run beside the big interior kernels: it gets the highest
@@ -70,6 +72,7 @@ extern "C" fb_handle* fb_create(int device) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev_k0) != cudaSuccess || cudaEventCreate(&h->ev_k1) != cudaSuccess) {
@@ -95,6 +98,8 @@ extern "C" void fb_destroy(fb_handle* h) {
   cudaEventDestroy(h->ev_k1);
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->stream2);
+  if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
+  for (auto& e : h->ev_copy) if (e) cudaEventDestroy(e);
   delete h;
 }
 

@@ -39,8 +39,9 @@ struct EdgeJob {
 
 struct fb_handle {
   int device = 0, sm_count = 148;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_copy = nullptr;   // work, edge kernels (high priority), host->device staging
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  cudaEvent_t ev_copy[16] = {};   // one per in-flight host->device group (fb_psk_demod_batch pipelines copies and kernels)
   bool profiling = false, k_recorded = false;
   uint64_t launches = 0;
   std::string err;

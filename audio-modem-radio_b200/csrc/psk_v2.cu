@@ -801,6 +801,58 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   const size_t esz = dtype == FB_F32 ? 4 : dtype == FB_F64 ? 8 : 2;
   const int bps = d.bits_per_sym, dper = 32 / bps;
 
+  // ---- host samples, large batch: pipeline the host->device copy with the kernels --------------------------------------
+  // The batch is cut into up to 16 groups of whole recordings; group g+1 is copied on the copy stream while group g is
+  // demodulated (device-resident recursion on the work stream), so only the first group's copy is exposed.
+  if (!(flags & FB_SAMPLES_ON_DEVICE) && n_rec >= 8 && (size_t)offsets[n_rec] * esz >= ((size_t)256 << 20)) {
+    const uint64_t total = offsets[n_rec], total_out_b = out_offsets[n_rec];
+    int rc;
+    if ((rc = fb_ensure(h, h->in, (size_t)total * esz + 16))) return rc;
+    const bool host_out = !(flags & FB_OUT_ON_DEVICE);
+    uint8_t* d_out = out; uint64_t* d_out_len = out_len; int64_t* d_sync = sync_idx; int32_t* d_status = status;
+    if (host_out) {
+      if ((rc = fb_ensure(h, h->out, (size_t)total_out_b + 16))) return rc;
+      if ((rc = fb_ensure(h, h->out_len, (size_t)n_rec * 8))) return rc;
+      if ((rc = fb_ensure(h, h->sync_idx, (size_t)n_rec * 8))) return rc;
+      if ((rc = fb_ensure(h, h->status, (size_t)n_rec * 4))) return rc;
+      d_out = (uint8_t*)h->out.p; d_out_len = (uint64_t*)h->out_len.p; d_sync = (int64_t*)h->sync_idx.p; d_status = (int32_t*)h->status.p;
+    }
+    const int n_groups = std::min(16, n_rec / 4);
+    std::vector<int> first(n_groups + 1, n_rec);
+    first[0] = 0;
+    for (int g = 1, r = 0; g < n_groups; ++g) {                       // equal shares of the samples
+      const uint64_t want = total / n_groups * g;
+      while (r < n_rec && offsets[r] < want) ++r;
+      first[g] = std::max(r, first[g - 1]);
+    }
+    FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));               // the copy stream starts after earlier work on this handle
+    FB_CUDA(h, cudaStreamWaitEvent(h->stream_copy, h->ev_fork, 0));
+    for (int g = 0; g < n_groups; ++g) {
+      const int r0 = first[g], r1 = first[g + 1];
+      if (r1 <= r0) continue;
+      const uint64_t e0 = offsets[r0], e1 = offsets[r1];
+      FB_CUDA(h, cudaMemcpyAsync((char*)h->in.p + e0 * esz, (const char*)samples + e0 * esz, (size_t)(e1 - e0) * esz,
+                                 cudaMemcpyHostToDevice, h->stream_copy));
+      FB_CUDA(h, cudaEventRecord(h->ev_copy[g], h->stream_copy));
+    }
+    for (int g = 0; g < n_groups; ++g) {
+      const int r0 = first[g], r1 = first[g + 1];
+      if (r1 <= r0) continue;
+      FB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy[g], 0));
+      rc = fb_psk_demod_batch(h, dp, taps, slow_w, r1 - r0, h->in.p, offsets + r0, dtype, FB_SAMPLES_ON_DEVICE | FB_OUT_ON_DEVICE | FB_ASYNC,
+                              d_out, out_offsets + r0, d_out_len + r0, d_sync + r0, d_status + r0);
+      if (rc) return rc;
+    }
+    if (host_out) {
+      if (total_out_b) FB_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)total_out_b, cudaMemcpyDeviceToHost, h->stream));
+      FB_CUDA(h, cudaMemcpyAsync(out_len, d_out_len, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, h->stream));
+      FB_CUDA(h, cudaMemcpyAsync(sync_idx, d_sync, (size_t)n_rec * 8, cudaMemcpyDeviceToHost, h->stream));
+      FB_CUDA(h, cudaMemcpyAsync(status, d_status, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (!(flags & FB_ASYNC) || host_out) FB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FB_OK;
+  }
+
   // ---- tile geometry of the main kernel -------------------------------------------------------------
   int T = 0, P = 0, nthreads = PM_THREADS, ntp = d.nt, padl = 0;
   const int wlen = d.wcols * d.sps;
