@@ -120,9 +120,9 @@ __device__ __forceinline__ float2 map22(float4 m, float fr, float fi, float2 acc
 // window loads of a quarter warp (8 symbols per thread) hit 8 distinct 16-byte bank groups instead of 4
 __device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2); }
 
-// SPS > 0: samples per symbol known at compile time (even): the staging loop is fully unrolled with all
+// SPS > 0: samples per symbol (and, with PP > 0, the shared-memory row pitch) known at compile time (even): the staging loop is fully unrolled with all
 // of a thread's loads in flight before the first store; SPS == 0: runtime sps.
-template <typename TIn, int NT, int SPS>
+template <typename TIn, int NT, int SPS, int PP>
 __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   const int ns = d1 - d0 + 1;                       // symbols d0 .. d1
   const int64_t N = (int64_t)pl.n;
   float* X = smem;                                  // [sps][P]   X[j][c] = x[n0 + (ca + c) sps + j]
-  const int P = a.P;
+  const int P = PP ? PP : a.P;                      // PP > 0: row pitch known at compile time (immediate store / load offsets)
   const int ca = d0 - a.dh - PADL;                  // global column (== symbol index) of staged column 0
   const int cc = a.dh + PADL;                       // staged column of symbol d0
   const int64_t n_d0 = (int64_t)a.n0 + (int64_t)d0 * sps;              // sample index of symbol d0
@@ -502,14 +502,25 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     float nx = __shfl_down_sync(0xffffffffu, y[0].x, 1), nyv = __shfl_down_sync(0xffffffffu, y[0].y, 1);
     if (lane == 31 && warp + 1 < nwarp) { nx = s_y0[warp + 1].x; nyv = s_y0[warp + 1].y; }
     uint32_t part = 0;
+    if (a.bps == 2) {                                 // slicer specialised outside the unrolled loop (uniform branch)
 #pragma unroll
-    for (int i = 0; i < PM_CH; ++i) {
-      const float2 prev = y[i];
-      const float2 cur = (i + 1 < PM_CH) ? y[(i + 1) % PM_CH] : make_float2(nx, nyv);
-      // d = cur * conj(prev) * rho
-      const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
-      const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
-      part = (part << a.bps) | psk_decide<float>(dr, di, a.bps);
+      for (int i = 0; i < PM_CH; ++i) {
+        const float2 prev = y[i];
+        const float2 cur = (i + 1 < PM_CH) ? y[(i + 1) % PM_CH] : make_float2(nx, nyv);
+        // d = cur * conj(prev) * rho
+        const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
+        const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
+        part = (part << 2) | psk_decide<float>(dr, di, 2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PM_CH; ++i) {
+        const float2 prev = y[i];
+        const float2 cur = (i + 1 < PM_CH) ? y[(i + 1) % PM_CH] : make_float2(nx, nyv);
+        const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
+        const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y);
+        part = (part << 1) | (dr < 0.f ? 1u : 0u);
+      }
     }
     const int nd = d1 - d0;                           // multiple of 32
     if (a.bps == 2) {                                 // 16 bits per thread, 2 threads per word
@@ -766,16 +777,17 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
-#define FB_LAUNCH_MAIN(NTV, SPSV)                                                                                               \
-    do {                                                                                                                          \
-      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      psk_main_kernel<TIn, NTV, SPSV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
+#define FB_LAUNCH_MAIN(NTV, SPSV, PPV)                                                                                                \
+    do {                                                                                                                                \
+      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      psk_main_kernel<TIn, NTV, SPSV, PPV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
     } while (0)
-    if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10);                          // 9600 sym/s at 96 kHz
-    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0);
-    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0);
-    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0);
-    else FB_LAUNCH_MAIN(0, 0);
+    if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048);     // 9600 sym/s at 96 kHz, full-size tiles
+    else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0);
+    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0);
+    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0);
+    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0);
+    else FB_LAUNCH_MAIN(0, 0, 0);
 #undef FB_LAUNCH_MAIN
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
