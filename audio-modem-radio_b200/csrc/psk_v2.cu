@@ -22,7 +22,9 @@
 #include <stdlib.h>
 
 #define PM_CH 8              // columns (= symbols) per thread: FIR register tile and slow-pole scan chunk
+#ifndef PM_THREADS
 #define PM_THREADS 256
+#endif
 #ifndef PM_MINB
 #define PM_MINB 2
 #endif
@@ -889,6 +891,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     }
     if (T < 32) emulate_only = true;
     nthreads = ((T + 1 + PM_CH - 1) / PM_CH + 31) / 32 * 32;
+    if (const char* e = getenv("FB_PSK_EXTRA_SMEM_KB")) smem += (size_t)atoi(e) * 1024;   // occupancy experiments
   }
 
   // ---- per-recording plan ---------------------------------------------------------------------------------
