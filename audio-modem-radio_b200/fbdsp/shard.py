@@ -7,8 +7,9 @@ GPU box (torch.distributed.gather_object), over gloo in the CPU tests.  Results 
 recording order, identical for every world size and shard order (tests/test_shard_gloo.py).
 
 Partitioning is longest-processing-time-first bin packing on sample counts (cost is linear in samples).
-The multi-part join that follows is the reference's FileAssembly semantics (decoder.py:20-116): parts ordered by
-part number, duplicates dropped, size and CRC32 of the joined file checked against the frame header.
+The multi-part join that follows is the reference's FileAssembly semantics (decoder.py:20-116, fbdsp/assembly.py): parts
+ordered by part number, duplicates replaced only by strictly higher-quality copies, size and CRC32 of the joined file
+checked against the frame header.
 """
 from __future__ import annotations
 
@@ -65,29 +66,27 @@ def decode_sharded(recordings: Sequence, lengths: Sequence[int], decode_fn: Call
 
 
 def assemble_parts(frames: Sequence[dict]) -> Dict[str, dict]:
-    """Join multi-part files from parsed frames ({'name','data','final_crc','part','total','file_size'}).
-
-    FileAssembly semantics (decoder.py:56-104): a file is keyed by (base name, file CRC); the first copy of a part is
-    kept; a file is complete when all `total` parts are present; the joined bytes are checked against file_size and
-    the CRC32 in the header.  Returns {key: {'data' | None, 'complete', 'size_ok', 'crc_ok', 'missing'}}.
-    """
-    files: Dict[str, dict] = {}
+    """Join multi-part files from parsed frames ({'name','data','final_crc','part','total','file_size'}) gathered from
+    all ranks: fbdsp.assembly.FileAssembly (the reference's semantics, decoder.py:20-116: part slots, a later copy of a
+    part replaces the stored one only when its signal quality is strictly higher, size / CRC32 of the joined file checked
+    against the frame header).  Parts are named "<file>.partN" by the sender (encoder.py:149), so the file is keyed by
+    the base name + file CRC.  Returns {key: {'name','data' | None,'complete','size_ok','crc_ok','missing'}}."""
+    from .assembly import FileAssembly
+    files: Dict[str, FileAssembly] = {}
     for fr in frames:
         name = fr["name"]
-        base = name.rsplit(".part", 1)[0] if ".part" in name else name       # encoder.py:149 names parts "<file>.partN"
+        base = name.rsplit(".part", 1)[0] if ".part" in name else name
         key = f"{base}_{fr['final_crc']}"                                       # decoder.py:251
-        f = files.setdefault(key, {"name": base, "total": int(fr.get("total", 1)), "file_size": int(fr.get("file_size", 0)),
-                                   "file_crc": int(fr["final_crc"]), "parts": {}})
-        p = int(fr.get("part", 0))
-        if 0 <= p < f["total"] and p not in f["parts"]:                         # decoder.py:58,62 (first copy wins here)
-            f["parts"][p] = fr["data"]
+        asm = files.get(key)
+        if asm is None:
+            asm = files[key] = FileAssembly(base, int(fr.get("total", 1)), int(fr.get("file_size", 0)), int(fr["final_crc"]))
+        asm.add_part(int(fr.get("part", 0)), fr["data"])
     out = {}
-    for key, f in files.items():
-        missing = [i for i in range(f["total"]) if i not in f["parts"]]
+    for key, asm in files.items():
+        missing = asm.get_missing_parts()
         if missing:
-            out[key] = {"name": f["name"], "data": None, "complete": False, "size_ok": False, "crc_ok": False, "missing": missing}
+            out[key] = {"name": asm.filename, "data": None, "complete": False, "size_ok": False, "crc_ok": False, "missing": missing}
             continue
-        data = b"".join(f["parts"][i] for i in range(f["total"]))               # decoder.py:95
-        out[key] = {"name": f["name"], "data": data, "complete": True, "size_ok": len(data) == f["file_size"],
-                    "crc_ok": (binascii.crc32(data) & 0xFFFFFFFF) == f["file_crc"], "missing": []}
+        data = asm.assemble_file()
+        out[key] = {"name": asm.filename, "data": data, "complete": True, "missing": [], **asm.check(data)}
     return out

@@ -247,3 +247,7 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# tests/golden/assembly.json (FileAssembly vectors, decoder.py:20-116) was generated by the snippet in
+# tests/test_assembly.py's docstring against the same unmodified reference import (import_reference()).
