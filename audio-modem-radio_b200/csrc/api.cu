@@ -88,6 +88,7 @@ extern "C" void fb_destroy(fb_handle* h) {
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->stream2);
   fb_fsk_release(h);
+  fb_resample_release(h);
   DevBuf* bufs[] = {&h->in, &h->out, &h->out_len, &h->sync_idx, &h->status, &h->bits, &h->plans, &h->tile_first, &h->tiles,
                     &h->jobs, &h->scratch, &h->taps, &h->slow_w, &h->sync_raw, &h->fec_in, &h->fec_out, &h->fec_meta, &h->misc};
   for (DevBuf* b : bufs)

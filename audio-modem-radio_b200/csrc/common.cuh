@@ -64,6 +64,7 @@ struct fb_handle {
 
 int fb_ensure(fb_handle* h, DevBuf& b, size_t bytes);
 void fb_fsk_release(fb_handle* h);   // fsk_v2.cu: cuFFT plans cached per handle
+void fb_resample_release(fb_handle* h);   // resample.cu: cuFFT plans cached per handle
 
 // bits back end (backend.cu): first-occurrence magic search + shifted byte packing
 int fb_bits_backend(fb_handle* h, int n_rec, const RecPlan* d_plans, const std::vector<RecPlan>& plans, int bps,

@@ -114,25 +114,24 @@ def decode_from_buffer(data, mode: str, symbol_rate) -> list:
 
 
 def read_wav(path: str):
-    """What soundfile.read hands decoder.decode_wav_file (decoder.py:381-382): first channel, PCM16 scaled by 1/32768.
-    Returned as the raw int16 samples (the engine's FB_S16 ingest applies the same scaling on the device)."""
+    """The PCM16 frames soundfile.read would scale for decoder.decode_wav_file (decoder.py:381): int16 array of shape
+    (frames,) or (frames, channels), and the sample rate.  Channel selection and the 1/32768 scaling happen on the device."""
     with wave.open(path, "rb") as w:
         sr, nch, sw = w.getframerate(), w.getnchannels(), w.getsampwidth()
         raw = w.readframes(w.getnframes())
     if sw != 2:
         raise ValueError("only PCM16 WAV is supported")
     pcm = np.frombuffer(raw, dtype="<i2")
-    if nch > 1:
-        pcm = np.ascontiguousarray(pcm.reshape(-1, nch)[:, 0])
-    return pcm, sr
+    return (pcm.reshape(-1, nch) if nch > 1 else pcm), sr
 
 
 def _wav_samples(path: str):
     pcm, sr = read_wav(path)
-    if sr != SAMPLE_RATE:               # decoder.py:385-387 (FFT resampler; host-side scipy until the device one lands)
-        from scipy import signal
-        x = pcm.astype(np.float64) / 32768.0
-        return signal.resample(x, int(round(len(x) * float(SAMPLE_RATE) / sr)))
+    if sr != SAMPLE_RATE:               # decoder.py:385-387: FFT resampler, on the device (csrc/resample.cu)
+        n = pcm.shape[0]
+        return default_engine().ingest_resample(pcm, int(round(n * float(SAMPLE_RATE) / sr)))
+    if pcm.ndim > 1:
+        pcm = np.ascontiguousarray(pcm[:, 0])                                                    # decoder.py:382
     return pcm
 
 

@@ -84,6 +84,21 @@ class Engine:
     def sync(self):
         _lib.check(self.lib, self.handle, self.lib.fb_sync(self.handle), "fb_sync")
 
+    # ------------------------------------------------------------------ WAV ingest
+    def ingest_resample(self, frames: np.ndarray, n_out: int) -> np.ndarray:
+        """Channel 0 of interleaved frames (int16 PCM / float32 / float64; shape (n,) or (n, channels)) as float64,
+        resampled to n_out samples with scipy.signal.resample's FFT method on the device (decoder.py:381-387)."""
+        a = np.ascontiguousarray(frames)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        if np.dtype(a.dtype) not in _DT:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        n, nch = a.shape
+        out = np.empty(int(n_out), dtype=np.float64)
+        rc = self.lib.fb_ingest_resample(self.handle, a.ctypes.data, n, nch, _DT[np.dtype(a.dtype)], int(n_out), out.ctypes.data, 0)
+        _lib.check(self.lib, self.handle, rc, "fb_ingest_resample")
+        return out
+
     # ------------------------------------------------------------------ DPSK
     def psk_demod_raw(self, d: PskDesign, samples_ptr: int, offsets: np.ndarray, dtype: int, flags: int,
                       out_ptr: int, out_offsets: np.ndarray, out_len_ptr: int, sync_ptr: int, status_ptr: int):

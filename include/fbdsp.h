@@ -173,6 +173,15 @@ int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw, const uin
                           const uint64_t* raw_len, int max_frames, fb_frame* frames, int32_t* n_frames,
                           uint64_t* payload_bytes, int flags);
 
+/* ---- WAV ingest on the device: replaces the host steps of decode_wav_file (decoder.py:381-387) ---------------------------
+ * in: n_frames interleaved frames of n_channels samples (FB_S16 = WAV PCM16, scaled by 1/32768 as soundfile does; FB_F32;
+ * FB_F64); channel 0 is kept (data[:, 0], decoder.py:382).  out: n_out float64 samples = scipy.signal.resample(channel0,
+ * n_out) (FFT method, decoder.py:385-387: n_out = int(round(n_frames * 96000 / sr))); n_out == n_frames just converts.
+ * FB_SAMPLES_ON_DEVICE / FB_OUT_ON_DEVICE say where in / out live; the result can be fed to the *_demod_batch calls as
+ * FB_F64 without leaving the device.                                                                                  */
+int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frames, int n_channels, int dtype, uint64_t n_out,
+                       double* out, int flags);
+
 #ifdef __cplusplus
 }
 #endif
