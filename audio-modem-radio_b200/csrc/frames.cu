@@ -29,11 +29,37 @@ __global__ void __launch_bounds__(FB_THREADS) parse_frames_kernel(const ParseRec
   if (threadIdx.x == 0) n_cand = 0;
   crc_tables_init(tab);
   // ---- (1) all offsets i with p[i..i+4) == "FBPC" (overlapping; the pattern cannot overlap itself) ----------
-  for (uint64_t i = threadIdx.x; i + 4 <= len; i += blockDim.x) {
-    if (p[i] == 'F' && p[i + 1] == 'B' && p[i + 2] == 'P' && p[i + 3] == 'C') {
+  // 16 bytes per thread and step (one LDG.128 once the pointer is aligned) plus the 3-byte look-ahead from the next
+  // chunk; four steps unrolled so several loads are in flight per thread (the byte-per-lane loop was latency-bound).
+  {
+    const uint64_t head = min(len, (uint64_t)((16 - ((uintptr_t)p & 15)) & 15));       // bytes before the first 16-byte boundary
+    auto hit = [&](uint64_t i) {
       const int slot = atomicAdd(&n_cand, 1);
       if (slot < MAX_CAND) cand[slot] = i;
+    };
+    for (uint64_t i = threadIdx.x; i < head && i + 4 <= len; i += blockDim.x)
+      if (p[i] == 'F' && p[i + 1] == 'B' && p[i + 2] == 'P' && p[i + 3] == 'C') hit(i);
+    const uint64_t nchunk = (len - head) / 16;                                          // whole aligned chunks
+    const uint4* q = reinterpret_cast<const uint4*>(p + head);
+#pragma unroll 4
+    for (uint64_t c = threadIdx.x; c < nchunk; c += blockDim.x) {
+      const uint4 v = __ldg(q + c);
+      const uint64_t base = head + c * 16;
+      uint32_t nxt = 0;                                                                 // the 3 bytes after this chunk
+      if (c + 1 < nchunk) nxt = __ldg(reinterpret_cast<const uint32_t*>(q + c + 1));
+      else {
+        for (int k = 0; k < 3; ++k) if (base + 16 + k < len) nxt |= (uint32_t)p[base + 16 + k] << (8 * k);
+      }
+      const uint32_t w[5] = {v.x, v.y, v.z, v.w, nxt};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int wi = k >> 2, sh = (k & 3) * 8;
+        const uint32_t four = sh ? (w[wi] >> sh) | (w[wi + 1] << (32 - sh)) : w[wi];
+        if (four == 0x43504246u && base + k + 4 <= len) hit(base + k);                  // "FBPC" little-endian
+      }
     }
+    for (uint64_t i = head + nchunk * 16 + threadIdx.x; i + 4 <= len; i += blockDim.x)  // ragged tail (< 16 bytes)
+      if (p[i] == 'F' && p[i + 1] == 'B' && p[i + 2] == 'P' && p[i + 3] == 'C') hit(i);
   }
   __syncthreads();
   const int nc = min(n_cand, MAX_CAND);
