@@ -319,12 +319,12 @@ def main():
         torch.cuda.synchronize()
 
     eng.lib.fb_set_profiling(eng.handle, 1)
+    clocks = ClockSampler(local)                      # nvidia-smi needs ~0.2 s to deliver its first sample: start it before
+    clocks.start()                                    # the warm-up so the (short) timed region is covered
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = eng.kernel_launches
-    clocks = ClockSampler(local)
-    clocks.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kernel_ms = []
     barrier()
@@ -341,6 +341,10 @@ def main():
         step()
         kernel_ms.append(float(eng.lib.fb_kernel_ms(eng.handle)))
     barrier()
+    t_load = time.perf_counter()
+    while len(clocks.lines) < 5 and time.perf_counter() - t_load < 3.0:      # keep the GPU under the same load until the
+        step()                                                               # sampler has a few readings (untimed)
+        eng.sync()
     clk = clocks.stop()
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
