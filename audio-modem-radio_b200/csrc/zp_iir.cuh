@@ -67,20 +67,28 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_fwd_kernel(const void* samples,
 #pragma unroll
   for (int i = 0; i < ORD; ++i) z[i] = 0.0;
   const int sg = tid >> 4, su = tid & 15;
-  for (int kb = -W16; kb < L; kb += ZP_EB) {
-    // positions touched by this block: [cb*L + kb, (cb+63)*L + kb + 15]
+  auto is_inner = [&](int kb) {                                     // all 64 x 16 positions of block kb are plain samples
     const int64_t e_lo = cb * L + kb, e_hi = (cb + ZP_THREADS - 1) * L + kb + ZP_EB - 1;
-    const bool inner = (e_lo - t.pad >= 0) && (e_hi - t.pad <= N - 1) && (e_lo > 0);
-    if (inner) {
-      const TIn* p = xin + (e_lo + (int64_t)sg * L + su - t.pad);
+    return kb < L && (e_lo - t.pad >= 0) && (e_hi - t.pad <= N - 1) && (e_lo > 0);
+  };
+  auto load_inner = [&](int kb, double (&v)[ZP_EB]) {               // this thread's share of the cooperative load
+    const TIn* p = xin + (cb * L + kb + (int64_t)sg * L + su - t.pad);
+    const int64_t stride = 4 * (int64_t)L;
 #pragma unroll
-      for (int i = 0; i < ZP_EB; ++i) {
-        double v;
-        if (sizeof(TIn) == 2) v = (double)__ldg(reinterpret_cast<const int16_t*>(p)) * (1.0 / 32768.0);
-        else v = (double)__ldg(p);
-        xs[sg + 4 * i][su] = v;
-        p += 4 * (int64_t)L;
-      }
+    for (int i = 0; i < ZP_EB; ++i) {
+      if (sizeof(TIn) == 2) v[i] = (double)__ldg(reinterpret_cast<const int16_t*>(p)) * (1.0 / 32768.0);
+      else v[i] = (double)__ldg(p);
+      p += stride;
+    }
+  };
+  double pre[ZP_EB];                                                // next block's inputs, in flight during this block's math
+  bool pre_ok = is_inner(-W16);
+  if (pre_ok) load_inner(-W16, pre);
+  for (int kb = -W16; kb < L; kb += ZP_EB) {
+    const bool inner = pre_ok;
+    if (inner) {
+#pragma unroll
+      for (int i = 0; i < ZP_EB; ++i) xs[sg + 4 * i][su] = pre[i];
     } else {
       for (int idx = tid; idx < ZP_THREADS * ZP_EB; idx += ZP_THREADS) {
         const int seg = idx >> 4, u = idx & 15;
@@ -89,12 +97,15 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_fwd_kernel(const void* samples,
       }
     }
     __syncthreads();
+    pre_ok = is_inner(kb + ZP_EB);
+    if (pre_ok) load_inner(kb + ZP_EB, pre);
     if (inner) {
       double* q = yp + (int64_t)kb * nch;
 #pragma unroll
       for (int u = 0; u < ZP_EB; ++u) {
         const double yv = zp_step<ORD>(t, z, xs[tid][u]);
-        if (kb >= 0) q[(int64_t)u * nch] = yv;
+        if (kb >= 0) *q = yv;
+        q += nch;
       }
     } else if (ch < nch) {
 #pragma unroll
@@ -132,12 +143,19 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_bwd_kernel(const double* ybase,
   const int sg = tid >> 4, su = tid & 15;
   // every position of every chunk of this CTA (warm-up included) strictly below the right end, outputs inside [0, N)
   const bool inner = ((cb + ZP_THREADS) * L + W16 < Next - 1) && (cb * L - t.pad >= 0) && ((cb + ZP_THREADS) * L - 1 - t.pad <= N - 1);
+  auto load_y = [&](int kb, double (&v)[ZP_EB]) {                   // own chunk, or (warm-up) the head of the next chunk
+    const double* q = kb >= L ? yp + 1 + (int64_t)(kb - L) * nch : yp + (int64_t)kb * nch;
+#pragma unroll
+    for (int u = 0; u < ZP_EB; ++u) { v[u] = *q; q += nch; }
+  };
+  double pre[ZP_EB];
+  if (inner) load_y(L + W16 - ZP_EB, pre);
   for (int kb = L + W16 - ZP_EB; kb >= 0; kb -= ZP_EB) {          // positions c0 + kb + 15 down to c0 + kb
     double yb[ZP_EB];
     if (inner) {
-      const double* q = kb >= L ? yp + 1 + (int64_t)(kb - L) * nch : yp + (int64_t)kb * nch;   // warm-up: head of the next chunk
 #pragma unroll
-      for (int u = 0; u < ZP_EB; ++u) yb[u] = q[(int64_t)u * nch];
+      for (int u = 0; u < ZP_EB; ++u) yb[u] = pre[u];
+      if (kb >= ZP_EB) load_y(kb - ZP_EB, pre);                     // next block's values in flight during this block's math
 #pragma unroll
       for (int u = ZP_EB - 1; u >= 0; --u) os[tid][u] = zp_step<ORD>(t, z, yb[u]);
     } else {
@@ -167,8 +185,9 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_bwd_kernel(const double* ybase,
     if (kb < L) {
       if (inner) {
         TOut* o = op + (cb * L + kb + (int64_t)sg * L + su - t.pad);
+        const int64_t stride = 4 * (int64_t)L;
 #pragma unroll
-        for (int i = 0; i < ZP_EB; ++i) { *o = (TOut)os[sg + 4 * i][su]; o += 4 * (int64_t)L; }
+        for (int i = 0; i < ZP_EB; ++i) { *o = (TOut)os[sg + 4 * i][su]; o += stride; }
       } else {
         for (int idx = tid; idx < ZP_THREADS * ZP_EB; idx += ZP_THREADS) {
           const int seg = idx >> 4, u = idx & 15;
