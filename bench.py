@@ -472,7 +472,7 @@ def main():
                         "so >= 6.1 ms at the measured 124 FMA/clk/SM (DESIGN.md 4); traffic = ncu dram bytes of the same "
                         "kernel per launch, scaled from the 32-recording capture in profiles/"}
     try:      # dram__bytes_read+write per sample from the committed ncu capture (profiles/r01_psk_main_ncu.txt)
-        for ln in open(os.path.join(ROOT, "profiles", "r01_psk_main_v5c_ncu.txt")):
+        for ln in open(os.path.join(ROOT, "profiles", "r01_psk_main_ncu.txt")):
             if ln.startswith("dram_bytes_per_sample"):
                 roofline["traffic"] = float(ln.split()[1]) * n_rec * n_samp
     except Exception:      # noqa: BLE001
