@@ -134,3 +134,45 @@ def test_digital_silence_deviation(engine):
     for b in bad:
         assert margin[b // 2] < 1e-5 or mag[b // 2] < 1e-14 * mag.max(), (b, margin[b // 2], mag[b // 2] / mag.max())
     assert [f["data"] for f in parse_fbp_stream_enhanced(res.raw)] == [f["data"] for f in parse_fbp_stream(st["raw"])]
+
+
+def test_config2_multipart_ofdm8_fec_pipeline(engine):
+    """BASELINE config 3 ("OFDM8 + fec.py decode of a multi-part file") at reduced scale, every stage on the device through
+    the C ABI: file -> parts -> ReedSolomonFEC.encode (oracle, TX side) -> FBPC frame per part -> ofdm_modulate_simple
+    (= DQPSK, modem.py:371) -> [GPU] batch demod (ofdm_demodulate_simple alias) -> frame parse + CRC32 -> RS decode ->
+    FileAssembly join -> whole-file size and CRC32; parts arrive shuffled and one of them twice."""
+    import binascii
+    import fbdsp
+    from oracle import fec as ofec
+    from oracle.frames import frame_data
+    from fbdsp.frames import parse_batch
+    from fbdsp.fec import rs_decode_batch
+    from fbdsp.assembly import assemble_stream
+    rng = np.random.default_rng(2072)
+    blob = rng.integers(0, 256, 9000, dtype=np.uint8).tobytes()
+    crc = binascii.crc32(blob) & 0xFFFFFFFF
+    part_size = 2048                                            # encoder.py:137 sizes parts by airtime; any size joins the same way
+    chunks = [blob[i:i + part_size] for i in range(0, len(blob), part_size)]
+    recs = []
+    for i, ch in enumerate(chunks):
+        coded = ofec.rs_encode(ch)                              # fec.py:11-32
+        framed = frame_data("big.bin", coded, i, len(chunks), len(blob), crc)
+        # four filler bytes after the frame: the very last differential symbol of a record has no successor to be decided
+        # against (the reference loses the last byte of a frame that ends exactly with the recording, too)
+        x = sig.qpsk_modulate(framed + b"\x00" * 4, baud=9600, carrier=9600.0)
+        x = x + rng.standard_normal(len(x)) * np.sqrt(np.mean(x * x) / 10 ** (20 / 10))
+        recs.append(x.astype(np.float32))
+    order = [3, 0, 4, 1, 1, 2]                                  # shuffled arrival, part 1 twice
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)  # ofdm_demodulate_simple(s, 9600, 9600.0, 8) -> qpsk_demodulate
+    res = engine.psk_demod_batch([recs[i] for i in order], d)
+    for i, r in zip(order, res):
+        assert r.raw == o2.ofdm_demodulate_simple(recs[i], 9600, 9600.0, 8)
+    frames = [f for fl in parse_batch([r.raw for r in res], engine, full=True) for f in fl]
+    assert len(frames) == len(order)
+    decoded = rs_decode_batch([f["data"] for f in frames], engine)
+    for f, (data, crc_ok) in zip(frames, decoded):
+        assert crc_ok and data == ofec.rs_decode(f["data"])
+        f["data"] = data[: part_size] if f["part"] < len(chunks) - 1 else data[: len(blob) - part_size * (len(chunks) - 1)]
+    files = assemble_stream(frames)
+    (f,) = [v for v in files.values() if v["complete"]]
+    assert f["data"] == blob and f["size_ok"] and f["crc_ok"]
