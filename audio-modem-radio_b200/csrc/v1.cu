@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <type_traits>
 
 enum { V1_BPSK = 0, V1_QPSK = 1, V1_PSK8 = 2, V1_OFDM = 3, V1_FSK = 4 };
 #define V1_THREADS 256
@@ -124,6 +125,48 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
   }
 }
 
+// The producer thread of a persistent CTA: walks tiles [t_begin, t_end) and brings each into the shared-memory ring.
+template <typename TIn>
+__device__ __forceinline__ void v1_produce(const V1Args& a, unsigned char* raw, V1Tile* desc, uint32_t full_s, uint32_t empty_s,
+                                           uint32_t t_begin, uint32_t t_end) {
+  int lo = 0, hi = a.n_rec;                                                // largest r with tile_first[r] <= t_begin
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(&a.tile_first[mid]) <= t_begin) lo = mid; else hi = mid; }
+  int rec = lo;
+  RecPlan pl = a.plans[rec];
+  int k0 = (int)(t_begin - __ldg(&a.tile_first[rec])) * a.S;
+  int st = 0;
+  uint32_t ph = 1;                                                        // parity of the previous round of `empty`
+  bool wrapped = false;
+  for (uint32_t t = t_begin; t < t_end; ++t) {
+    while (k0 >= pl.nsym) { pl = a.plans[++rec]; k0 = 0; }                 // next recording that has symbols
+    if (wrapped) mbar_wait<true>(empty_s + 8 * st, ph);
+    const int ns = min(a.S, pl.nsym - k0);
+    // bytes [b0, b1) of the batch buffer, widened to 16-byte boundaries (never past the buffer's last whole 16 bytes)
+    const uint64_t b0 = (pl.off + (uint64_t)k0 * a.sps) * sizeof(TIn), b1 = b0 + (uint64_t)ns * a.sps * sizeof(TIn);
+    const uint64_t a0 = b0 & ~15ull;
+    uint64_t a1 = min((b1 + 15) & ~15ull, a.total_bytes & ~15ull);
+    if (a1 < a0) a1 = a0;
+    unsigned char* dst = raw + (size_t)st * a.raw_bytes;
+    for (uint64_t g = max(a1, b0); g < b1; ++g) dst[g - a0] = __ldg(reinterpret_cast<const unsigned char*>(a.samples) + g);
+    V1Tile d;
+    d.out_off = pl.out_off; d.out_cap = pl.out_cap; d.word_off = pl.word_off;
+    d.nsym = pl.nsym; d.k0 = k0; d.ns = ns; d.skew = (int)(b0 - a0);
+    desc[st] = d;
+    const uint32_t fb = full_s + 8 * st;
+    if (a1 > a0) {
+      const uint32_t nbytes = (uint32_t)(a1 - a0);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(nbytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<const unsigned char*>(a.samples) + a0),
+                     "r"(nbytes), "r"(fb) : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+    }
+    k0 += a.S;
+    if (++st == a.stages) { st = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
+  }
+}
+
 template <typename TIn, int NFU>
 __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a) {
   extern __shared__ __align__(128) unsigned char v1_smem[];
@@ -153,43 +196,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 
   if (tid >= V1_THREADS) {
     // ================================ producer (one thread) ================================
-    if (tid != V1_THREADS || t_begin >= t_end) return;
-    int lo = 0, hi = a.n_rec;                                                // largest r with tile_first[r] <= t_begin
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(&a.tile_first[mid]) <= t_begin) lo = mid; else hi = mid; }
-    int rec = lo;
-    RecPlan pl = a.plans[rec];
-    int k0 = (int)(t_begin - __ldg(&a.tile_first[rec])) * a.S;
-    int st = 0;
-    uint32_t ph = 1;                                                        // parity of the previous round of `empty`
-    bool wrapped = false;
-    for (uint32_t t = t_begin; t < t_end; ++t) {
-      while (k0 >= pl.nsym) { pl = a.plans[++rec]; k0 = 0; }                 // next recording that has symbols
-      if (wrapped) mbar_wait<true>(empty_s + 8 * st, ph);
-      const int ns = min(a.S, pl.nsym - k0);
-      // bytes [b0, b1) of the batch buffer, widened to 16-byte boundaries (never past the buffer's last whole 16 bytes)
-      const uint64_t b0 = (pl.off + (uint64_t)k0 * a.sps) * sizeof(TIn), b1 = b0 + (uint64_t)ns * a.sps * sizeof(TIn);
-      const uint64_t a0 = b0 & ~15ull;
-      uint64_t a1 = min((b1 + 15) & ~15ull, a.total_bytes & ~15ull);
-      if (a1 < a0) a1 = a0;
-      unsigned char* dst = raw + (size_t)st * a.raw_bytes;
-      for (uint64_t g = max(a1, b0); g < b1; ++g) dst[g - a0] = __ldg(reinterpret_cast<const unsigned char*>(a.samples) + g);
-      V1Tile d;
-      d.out_off = pl.out_off; d.out_cap = pl.out_cap; d.word_off = pl.word_off;
-      d.nsym = pl.nsym; d.k0 = k0; d.ns = ns; d.skew = (int)(b0 - a0);
-      desc[st] = d;
-      const uint32_t fb = full_s + 8 * st;
-      if (a1 > a0) {
-        const uint32_t nbytes = (uint32_t)(a1 - a0);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(nbytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<const unsigned char*>(a.samples) + a0),
-                       "r"(nbytes), "r"(fb) : "memory");
-      } else {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
-      }
-      k0 += a.S;
-      if (++st == a.stages) { st = 0; ph = wrapped ? ph ^ 1u : 0u; wrapped = true; }
-    }
+    if (tid == V1_THREADS && t_begin < t_end) v1_produce<TIn>(a, raw, desc, full_s, empty_s, t_begin, t_end);
     return;
   }
 
@@ -316,6 +323,157 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
       }
       asm volatile("bar.sync 1, %0;" ::"n"(V1_THREADS) : "memory");             // codes may be overwritten by the next tile
     }
+    if (++st == a.stages) { st = 0; ph ^= 1u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ specialised correlator
+// Same persistent producer / consumer ring as v1_corr_kernel, with the symbol geometry at compile time (the parameter
+// sets of the v1 decoder map, App. B.9) and float32 samples:
+//   * the correlator rows travel as a __grid_constant__ kernel parameter, so every weight is a constant-bank operand of
+//     its DFMA -- no weight loads at all (the generic kernel re-reads NFU double2 per sample from shared memory, which
+//     is what bounded OFDM8: 4 LDS.128 + 1 LDS.32 per sample)
+//   * a thread reads its symbol with VEC-wide aligned loads (VEC = 2 for sps 10 / 2, 4 for sps 20: bank-conflict free at
+//     those strides; odd sps keeps scalar loads, conflict-free by itself); the sub-vector phase of the symbol start is
+//     uniform over a tile (sps % VEC == 0), so the register shift is a warp-uniform switch
+//   * 32 symbols of a warp are always BPSYM whole words: redux.sync OR for BPSYM <= 4, a shuffle gather for wider codes
+//     (OFDM8's 14 bits, 8PSK's 3) -- no shared-memory code table and no CTA barrier for any mode
+struct V1Weights { double2 w[64]; };          // [j * NFU + m], unique rows only
+
+// B.6 with two cross products on the folded angle phi' = atan2(|Q|, |I|) (sector edges pi/8 and 3 pi/8), same 1e-12
+// guard band as psk8_code (inside it: the literal atan2 evaluation)
+__device__ __forceinline__ uint32_t psk8_code_folded(double I, double Q) {
+  const double c1 = 0.92387953251128674, s1 = 0.38268343236508977;
+  const double ai = fabs(I), aq = fabs(Q);
+  const double cr1 = c1 * aq - s1 * ai, cr3 = s1 * aq - c1 * ai;             // |v| sin(phi' - pi/8), |v| sin(phi' - 3 pi/8)
+  const double tol = 1e-12 * (ai + aq);
+  if (fabs(cr1) <= tol || fabs(cr3) <= tol) return psk8_code(I, Q);
+  const uint32_t o = (cr1 > 0.0 ? 1u : 0u) + (cr3 > 0.0 ? 1u : 0u);
+  const bool in = I < 0.0, qn = Q < 0.0;
+  // Q1: o | Q2 (phi = pi - phi'): 4 - o | Q3 (pi + phi'): 4 + o | Q4 (2 pi - phi'): 6 + [phi' < 3 pi/8]
+  return qn ? (in ? 4u + o : (o < 2u ? 7u : 6u)) : (in ? 4u - o : o);
+}
+
+template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF>
+__global__ void __launch_bounds__(V1_THREADS + 32) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
+  constexpr int BPSYM = MODE == V1_BPSK ? 1 : MODE == V1_QPSK ? 2 : MODE == V1_PSK8 ? 3 : MODE == V1_OFDM ? 2 * NF : 1;
+  constexpr int VEC = (SPS % 4 == 0) ? 4 : (SPS % 2 == 0) ? 2 : 1;
+  constexpr int NV = (LEN + 2 * (VEC - 1)) / VEC;                             // aligned vectors that cover any phase
+  static_assert(NFU * LEN <= 64, "weights exceed the parameter table");
+  extern __shared__ __align__(128) unsigned char v1_smem[];
+  __shared__ __align__(8) unsigned long long full[V1_STAGES], empty[V1_STAGES];
+  __shared__ V1Tile desc[V1_STAGES];
+  unsigned char* raw = v1_smem;
+  const int tid = threadIdx.x;
+  const uint32_t q = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t_begin = min(a.n_tiles, blockIdx.x * q), t_end = min(a.n_tiles, t_begin + q);
+  const uint32_t full_s = (uint32_t)__cvta_generic_to_shared(full), empty_s = (uint32_t)__cvta_generic_to_shared(empty);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < V1_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_s + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_s + 8 * s), "n"(V1_THREADS / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= V1_THREADS) {
+    if (tid == V1_THREADS && t_begin < t_end) v1_produce<float>(a, raw, desc, full_s, empty_s, t_begin, t_end);
+    return;
+  }
+  const int lane = tid & 31;
+  int st = 0;
+  uint32_t ph = 0;
+  for (uint32_t t = t_begin; t < t_end; ++t) {
+    mbar_wait<false>(full_s + 8 * st, ph);
+    const V1Tile d = desc[st];
+    const float* xs = reinterpret_cast<const float*>(raw + (size_t)st * a.raw_bytes);
+    const int ns = d.ns;
+    const int w_first = (d.skew >> 2) + OFF0;                                 // word index of symbol 0's first correlated sample
+    const int phase = w_first & (VEC - 1);                                    // same for every symbol of the tile
+    for (int s0 = 0; s0 < ns; s0 += V1_THREADS) {
+      const int s = s0 + tid;
+      const bool valid = s < ns;
+      double fr[NFU], fi[NFU];
+#pragma unroll
+      for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
+      if (valid) {
+        float x[NV * VEC];
+        const float* xp = xs + (w_first - phase) + s * SPS;                   // VEC-aligned
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (VEC == 4) { const float4 u = reinterpret_cast<const float4*>(xp)[v]; x[4 * v] = u.x; x[4 * v + 1] = u.y; x[4 * v + 2] = u.z; x[4 * v + 3] = u.w; }
+          else if (VEC == 2) { const float2 u = reinterpret_cast<const float2*>(xp)[v]; x[2 * v] = u.x; x[2 * v + 1] = u.y; }
+          else x[v] = xp[v];
+        }
+        auto corr = [&](auto PH) {
+          constexpr int P = decltype(PH)::value;
+#pragma unroll
+          for (int j = 0; j < LEN; ++j) {
+            const double xv = (double)x[j + P];
+#pragma unroll
+            for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
+          }
+        };
+        if (VEC == 1) corr(std::integral_constant<int, 0>{});
+        else if (VEC == 2) { if (phase) corr(std::integral_constant<int, VEC >= 2 ? 1 : 0>{}); else corr(std::integral_constant<int, 0>{}); }
+        else {
+          switch (phase) {
+            case 0: corr(std::integral_constant<int, 0>{}); break;
+            case 1: corr(std::integral_constant<int, VEC >= 4 ? 1 : 0>{}); break;
+            case 2: corr(std::integral_constant<int, VEC >= 4 ? 2 : 0>{}); break;
+            default: corr(std::integral_constant<int, VEC >= 4 ? 3 : 0>{}); break;
+          }
+        }
+      }
+      uint32_t code = 0;
+      if (valid) {
+        if (MODE == V1_QPSK) code = quadrant_code(fr[0], fi[0]);
+        else if (MODE == V1_BPSK) code = fr[0] > 0.0 ? 0u : 1u;
+        else if (MODE == V1_PSK8) code = psk8_code_folded(fr[0], fi[0]);
+        else if (MODE == V1_OFDM) {
+          uint32_t qq = 0, qc = 0;
+#pragma unroll
+          for (int u = 0; u < NFU; ++u) {
+            qq |= quadrant_code(fr[u], fi[u]) << (2 * u);
+            qc |= quadrant_code(fr[u], -fi[u]) << (2 * u);
+          }
+#pragma unroll
+          for (int m = 0; m < NF; ++m) {
+            const int mp = a.map[m];
+            code = (code << 2) | ((((mp & 0x100) ? qc : qq) >> (2 * (mp & 0xff))) & 3u);
+          }
+        } else {
+          constexpr int I1 = NFU > 1 ? 1 : 0;
+          const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
+          code = pm > ps ? 1u : 0u;
+        }
+      }
+      // ---- 32 symbols of this warp -> BPSYM words (stream bit of lane i's code: [i * BPSYM, (i + 1) * BPSYM), MSB first)
+      uint32_t mine = 0;
+      if (BPSYM <= 4) {
+        const int pbit = lane * BPSYM, wi = pbit >> 5;
+        const unsigned long long v64 = (unsigned long long)code << (64 - BPSYM - (pbit & 31));
+        const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+#pragma unroll
+        for (int k = 0; k < BPSYM; ++k) {
+          const uint32_t wk = __reduce_or_sync(0xffffffffu, (wi == k ? hi : 0u) | (wi + 1 == k ? lo : 0u));
+          if (lane == k) mine = wk;
+        }
+      } else {
+        constexpr int NT = (32 + BPSYM - 1) / BPSYM + 1;                      // symbols that can touch one word
+        const int i0 = (32 * lane) / BPSYM, skip = 32 * lane - i0 * BPSYM;    // lanes >= BPSYM gather garbage, never stored
+        unsigned long long acc = 0;
+#pragma unroll
+        for (int u = 0; u < NT; ++u) acc = (acc << BPSYM) | (unsigned long long)__shfl_sync(0xffffffffu, code, min(i0 + u, 31));
+        mine = (uint32_t)(acc >> (NT * BPSYM - 32 - skip));
+      }
+      const int sw = s0 + (tid & ~31);                                        // first symbol of this warp's 32
+      if (lane < BPSYM && sw * BPSYM + 32 * lane < ns * BPSYM)
+        v1_store_word(a, d, (uint64_t)(d.k0 + sw) * BPSYM / 32 + lane, mine);
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + 8 * st) : "memory");
     if (++st == a.stages) { st = 0; ph ^= 1u; }
   }
 }
@@ -480,6 +638,17 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   while (G < 32 && p.sps % (2 * G) == 0) G *= 2;
   G = std::max(1, G / 4);
   while (G > 1 && p.len / G < 4) G /= 2;
+  // compile-time geometries of v1_sym_kernel (float32 samples): id = index into the launch table below, -1 = generic kernel
+  int sym_id = -1;
+  if ((p.prefilter || dtype == FB_F32) && !getenv("FB_V1_GENERIC")) {
+    const bool psk = p.mode <= V1_PSK8 && p.off0 == 0 && p.len == p.sps && nfu == 1;
+    if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20)) sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : 6) + p.mode;
+    else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7) sym_id = 9;
+    else if (p.mode == V1_OFDM && p.sps == 20 && p.off0 == 5 && p.len == 15 && nfu == 4 && p.nf == 4) sym_id = 10;
+    else if (p.mode == V1_FSK && p.off0 == 0 && p.len == p.sps && nfu == 2 && (p.sps == 10 || p.sps == 5 || p.sps == 20))
+      sym_id = p.sps == 10 ? 11 : p.sps == 5 ? 12 : 13;
+  }
+  if (sym_id >= 0) G = 1;
   size_t tile_target = 20480;
   int stages = 2;
   if (const char* e = getenv("FB_V1_TILE")) tile_target = (size_t)std::max(1024, atoi(e));      // tuning knobs
@@ -488,8 +657,9 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   const int SP = std::max(32, V1_THREADS / G);
   int S = (int)std::min<size_t>(4096, (tile_target / ((size_t)p.sps * kesz)) / SP * SP);
   if (S < SP) S = (int)std::max<size_t>(32, std::min<size_t>(SP, (tile_target / ((size_t)p.sps * kesz)) / 32 * 32));
-  const size_t raw_bytes = ((size_t)S * p.sps * kesz + 16 + 127) / 128 * 128;
-  const size_t smem = stages * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
+  // +48: alignment skew of the bulk copy (<= 12) and the over-read of v1_sym_kernel's aligned vector loads
+  const size_t raw_bytes = ((size_t)S * p.sps * kesz + 48 + 127) / 128 * 128;
+  const size_t smem = sym_id >= 0 ? stages * raw_bytes + 128 : stages * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
   if (smem > 200 * 1024) return FB_EUNSUPPORTED;
   std::vector<RecPlan> plans(n_rec);
   std::vector<uint32_t> tile_first(n_rec + 1, 0);
@@ -608,7 +778,38 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
       if (NFU == 1) FB_V1_LAUNCH(T, 1); else if (NFU == 2) FB_V1_LAUNCH(T, 2);                     \
       else if (NFU == 4) FB_V1_LAUNCH(T, 4); else FB_V1_LAUNCH(T, 8);                              \
     } while (0)
-    if (kdtype == FB_F32) FB_V1_DISPATCH(float);
+    if (sym_id >= 0) {
+      V1Weights wt{};
+      for (int j = 0; j < p.len; ++j)
+        for (int m = 0; m < nfu; ++m) wt.w[j * nfu + m] = make_double2(utab[((size_t)m * p.len + j) * 2], utab[((size_t)m * p.len + j) * 2 + 1]);
+#define FB_V1_SYM(ID, ...)                                                                                              \
+      case ID: {                                                                                                        \
+        auto kern = v1_sym_kernel<__VA_ARGS__>;                                                                         \
+        FB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        int per_sm = 1;                                                                                                 \
+        FB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, V1_THREADS + 32, smem));                \
+        const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, per_sm) * (uint32_t)h->sm_count);       \
+        kern<<<grid, V1_THREADS + 32, smem, h->stream>>>(a, wt);                                                        \
+      } break;
+      switch (sym_id) {
+        FB_V1_SYM(0, V1_BPSK, 10, 0, 10, 1, 1)
+        FB_V1_SYM(1, V1_QPSK, 10, 0, 10, 1, 1)
+        FB_V1_SYM(2, V1_PSK8, 10, 0, 10, 1, 1)
+        FB_V1_SYM(3, V1_BPSK, 2, 0, 2, 1, 1)
+        FB_V1_SYM(4, V1_QPSK, 2, 0, 2, 1, 1)
+        FB_V1_SYM(5, V1_PSK8, 2, 0, 2, 1, 1)
+        FB_V1_SYM(6, V1_BPSK, 20, 0, 20, 1, 1)
+        FB_V1_SYM(7, V1_QPSK, 20, 0, 20, 1, 1)
+        FB_V1_SYM(8, V1_PSK8, 20, 0, 20, 1, 1)
+        FB_V1_SYM(9, V1_OFDM, 10, 2, 8, 4, 7)
+        FB_V1_SYM(10, V1_OFDM, 20, 5, 15, 4, 4)
+        FB_V1_SYM(11, V1_FSK, 10, 0, 10, 2, 1)
+        FB_V1_SYM(12, V1_FSK, 5, 0, 5, 2, 1)
+        FB_V1_SYM(13, V1_FSK, 20, 0, 20, 2, 1)
+        default: return FB_EINVAL;
+      }
+#undef FB_V1_SYM
+    } else if (kdtype == FB_F32) FB_V1_DISPATCH(float);
     else if (kdtype == FB_F64) FB_V1_DISPATCH(double);
     else FB_V1_DISPATCH(int16_t);
 #undef FB_V1_DISPATCH
