@@ -340,26 +340,42 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 //     (OFDM8's 14 bits, 8PSK's 3) -- no shared-memory code table and no CTA barrier for any mode
 struct V1Weights { double2 w[64]; };          // [j * NFU + m], unique rows only
 
-// B.6 with two cross products on the folded angle phi' = atan2(|Q|, |I|) (sector edges pi/8 and 3 pi/8), same 1e-12
-// guard band as psk8_code (inside it: the literal atan2 evaluation)
+__device__ __noinline__ uint32_t psk8_code_slow(double I, double Q) { return psk8_code(I, Q); }   // rare: keep it out of line
+
+// Decisions from sign bits.  A correlator accumulator starts at +0.0 and is a chain of round-to-nearest FMAs, so it is
+// never -0.0: "v < 0" is its sign bit, appended to `code` with one funnel shift.
+__device__ __forceinline__ uint32_t push_sign(uint32_t code, double v) { return __funnelshift_l((uint32_t)__double2hiint(v), code, 1); }
+
+// B.6 with two cross products on the folded angle phi' = atan2(|Q|, |I|) (sector edges pi/8 and 3 pi/8).  Symbols whose
+// cross product is within 2^-39 of max(|I|, |Q|) of an edge (hi-word integer compare; wider than psk8_code's 1e-12 band)
+// or that are zero / denormal take psk8_code, i.e. the literal atan2 evaluation.
 __device__ __forceinline__ uint32_t psk8_code_folded(double I, double Q) {
   const double c1 = 0.92387953251128674, s1 = 0.38268343236508977;
   const double ai = fabs(I), aq = fabs(Q);
   const double cr1 = c1 * aq - s1 * ai, cr3 = s1 * aq - c1 * ai;             // |v| sin(phi' - pi/8), |v| sin(phi' - 3 pi/8)
-  const double tol = 1e-12 * (ai + aq);
-  if (fabs(cr1) <= tol || fabs(cr3) <= tol) return psk8_code(I, Q);
-  const uint32_t o = (cr1 > 0.0 ? 1u : 0u) + (cr3 > 0.0 ? 1u : 0u);
-  const bool in = I < 0.0, qn = Q < 0.0;
+  const int h1 = __double2hiint(cr1), h3 = __double2hiint(cr3);
+  const int band = max(max(__double2hiint(I) & 0x7fffffff, __double2hiint(Q) & 0x7fffffff) - (39 << 20), 1);
+  if (((h1 & 0x7fffffff) < band) | ((h3 & 0x7fffffff) < band)) return psk8_code_slow(I, Q);
+  const uint32_t o = 2u - ((uint32_t)h1 >> 31) - ((uint32_t)h3 >> 31);       // edges below phi'
+  const bool in = __double2hiint(I) < 0, qn = __double2hiint(Q) < 0;
   // Q1: o | Q2 (phi = pi - phi'): 4 - o | Q3 (pi + phi'): 4 + o | Q4 (2 pi - phi'): 6 + [phi' < 3 pi/8]
   return qn ? (in ? 4u + o : (o < 2u ? 7u : 6u)) : (in ? 4u - o : o);
 }
 
-template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF>
-__global__ void __launch_bounds__(V1_THREADS + 32) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
+// SPT consecutive symbols per thread (sps 2: the per-warp packing and store are amortised over 4 symbols).
+// OFDM: bins m >= NFU are the conjugates of bins LEN - m - 2 (real input; the host checks its row map against this).
+// Non-finite samples: a NaN accumulator decides '10' per (I, Q) pair like the comparison chain of B.5 does; OFDM tests
+// the first bin only (scipy's FFT and a direct DFT spread an Inf differently anyway).
+template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF, int SPT>
+__global__ void __launch_bounds__(V1_THREADS + 32, 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
   constexpr int BPSYM = MODE == V1_BPSK ? 1 : MODE == V1_QPSK ? 2 : MODE == V1_PSK8 ? 3 : MODE == V1_OFDM ? 2 * NF : 1;
-  constexpr int VEC = (SPS % 4 == 0) ? 4 : (SPS % 2 == 0) ? 2 : 1;
-  constexpr int NV = (LEN + 2 * (VEC - 1)) / VEC;                             // aligned vectors that cover any phase
+  constexpr int BPT = BPSYM * SPT;                                            // bits per thread and pass
+  constexpr int STRIDE = SPS * SPT;                                           // samples between consecutive threads
+  constexpr int SPAN = (SPT - 1) * SPS + LEN;                                 // samples a thread correlates
+  constexpr int VEC = (STRIDE % 4 == 0) ? 4 : (STRIDE % 2 == 0) ? 2 : 1;
+  constexpr int NV = (SPAN + 2 * (VEC - 1)) / VEC;                            // aligned vectors that cover any phase
   static_assert(NFU * LEN <= 64, "weights exceed the parameter table");
+  static_assert(BPT <= 16, "code of one thread must fit the shuffle gather");
   extern __shared__ __align__(128) unsigned char v1_smem[];
   __shared__ __align__(8) unsigned long long full[V1_STAGES], empty[V1_STAGES];
   __shared__ V1Tile desc[V1_STAGES];
@@ -390,86 +406,85 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_sym_kernel(const V1Args a,
     const float* xs = reinterpret_cast<const float*>(raw + (size_t)st * a.raw_bytes);
     const int ns = d.ns;
     const int w_first = (d.skew >> 2) + OFF0;                                 // word index of symbol 0's first correlated sample
-    const int phase = w_first & (VEC - 1);                                    // same for every symbol of the tile
-    for (int s0 = 0; s0 < ns; s0 += V1_THREADS) {
-      const int s = s0 + tid;
-      const bool valid = s < ns;
-      double fr[NFU], fi[NFU];
-#pragma unroll
-      for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
-      if (valid) {
+    const int phase = w_first & (VEC - 1);                                    // same for every thread of the tile
+    for (int q0 = 0; q0 * SPT < ns; q0 += V1_THREADS) {
+      const int s = (q0 + tid) * SPT;                                         // first symbol of this thread
+      uint32_t code = 0;
+      if (s < ns) {
         float x[NV * VEC];
-        const float* xp = xs + (w_first - phase) + s * SPS;                   // VEC-aligned
+        const float* xp = xs + (w_first - phase) + (q0 + tid) * STRIDE;       // VEC-aligned
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           if (VEC == 4) { const float4 u = reinterpret_cast<const float4*>(xp)[v]; x[4 * v] = u.x; x[4 * v + 1] = u.y; x[4 * v + 2] = u.z; x[4 * v + 3] = u.w; }
           else if (VEC == 2) { const float2 u = reinterpret_cast<const float2*>(xp)[v]; x[2 * v] = u.x; x[2 * v + 1] = u.y; }
           else x[v] = xp[v];
         }
-        auto corr = [&](auto PH) {
+        auto decide = [&](auto PH) {
           constexpr int P = decltype(PH)::value;
 #pragma unroll
-          for (int j = 0; j < LEN; ++j) {
-            const double xv = (double)x[j + P];
+          for (int g = 0; g < SPT; ++g) {
+            double fr[NFU], fi[NFU];
 #pragma unroll
-            for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
+            for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) {
+              const double xv = (double)x[g * SPS + j + P];
+#pragma unroll
+              for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
+            }
+            uint32_t c = 0;
+            if (MODE == V1_QPSK) {                                            // B.5: bit 1 = Q < 0, bit 0 = I < 0
+              c = push_sign(push_sign(0u, fi[0]), fr[0]);
+              if (fr[0] != fr[0] || fi[0] != fi[0]) c = 2u;
+            } else if (MODE == V1_BPSK) c = fr[0] > 0.0 ? 0u : 1u;            // B.4: '0' if I > 0 else '1'
+            else if (MODE == V1_PSK8) c = psk8_code_folded(fr[0], fi[0]);
+            else if (MODE == V1_OFDM) {                                       // B.7: bins in order, (Im < 0, Re < 0) each
+#pragma unroll
+              for (int m = 0; m < NF; ++m) {
+                if (m < NFU) c = push_sign(push_sign(c, fi[m]), fr[m]);
+                else { const int u = LEN - m - 2; c = push_sign((c << 1) | (fi[u] > 0.0 ? 1u : 0u), fr[u]); }
+              }
+              if (fr[0] != fr[0] || fi[0] != fi[0]) c = 0xaaaaaaaau >> (32 - 2 * NF);
+            } else {
+              constexpr int I1 = NFU > 1 ? 1 : 0;
+              const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
+              c = pm > ps ? 1u : 0u;
+            }
+            code = (code << BPSYM) | ((SPT == 1 || s + g < ns) ? c : 0u);
           }
         };
-        if (VEC == 1) corr(std::integral_constant<int, 0>{});
-        else if (VEC == 2) { if (phase) corr(std::integral_constant<int, VEC >= 2 ? 1 : 0>{}); else corr(std::integral_constant<int, 0>{}); }
+        if (VEC == 1) decide(std::integral_constant<int, 0>{});
+        else if (VEC == 2) { if (phase) decide(std::integral_constant<int, VEC >= 2 ? 1 : 0>{}); else decide(std::integral_constant<int, 0>{}); }
         else {
           switch (phase) {
-            case 0: corr(std::integral_constant<int, 0>{}); break;
-            case 1: corr(std::integral_constant<int, VEC >= 4 ? 1 : 0>{}); break;
-            case 2: corr(std::integral_constant<int, VEC >= 4 ? 2 : 0>{}); break;
-            default: corr(std::integral_constant<int, VEC >= 4 ? 3 : 0>{}); break;
+            case 0: decide(std::integral_constant<int, 0>{}); break;
+            case 1: decide(std::integral_constant<int, VEC >= 4 ? 1 : 0>{}); break;
+            case 2: decide(std::integral_constant<int, VEC >= 4 ? 2 : 0>{}); break;
+            default: decide(std::integral_constant<int, VEC >= 4 ? 3 : 0>{}); break;
           }
         }
       }
-      uint32_t code = 0;
-      if (valid) {
-        if (MODE == V1_QPSK) code = quadrant_code(fr[0], fi[0]);
-        else if (MODE == V1_BPSK) code = fr[0] > 0.0 ? 0u : 1u;
-        else if (MODE == V1_PSK8) code = psk8_code_folded(fr[0], fi[0]);
-        else if (MODE == V1_OFDM) {
-          uint32_t qq = 0, qc = 0;
-#pragma unroll
-          for (int u = 0; u < NFU; ++u) {
-            qq |= quadrant_code(fr[u], fi[u]) << (2 * u);
-            qc |= quadrant_code(fr[u], -fi[u]) << (2 * u);
-          }
-#pragma unroll
-          for (int m = 0; m < NF; ++m) {
-            const int mp = a.map[m];
-            code = (code << 2) | ((((mp & 0x100) ? qc : qq) >> (2 * (mp & 0xff))) & 3u);
-          }
-        } else {
-          constexpr int I1 = NFU > 1 ? 1 : 0;
-          const double pm = fr[0] * fr[0] + fi[0] * fi[0], ps = fr[I1] * fr[I1] + fi[I1] * fi[I1];
-          code = pm > ps ? 1u : 0u;
-        }
-      }
-      // ---- 32 symbols of this warp -> BPSYM words (stream bit of lane i's code: [i * BPSYM, (i + 1) * BPSYM), MSB first)
+      // ---- 32 threads of this warp -> BPT words (stream bits of lane i's code: [i * BPT, (i + 1) * BPT), MSB first)
       uint32_t mine = 0;
-      if (BPSYM <= 4) {
-        const int pbit = lane * BPSYM, wi = pbit >> 5;
-        const unsigned long long v64 = (unsigned long long)code << (64 - BPSYM - (pbit & 31));
+      if (BPT <= 4) {
+        const int pbit = lane * BPT, wi = pbit >> 5;
+        const unsigned long long v64 = (unsigned long long)code << (64 - BPT - (pbit & 31));
         const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
 #pragma unroll
-        for (int k = 0; k < BPSYM; ++k) {
+        for (int k = 0; k < BPT; ++k) {
           const uint32_t wk = __reduce_or_sync(0xffffffffu, (wi == k ? hi : 0u) | (wi + 1 == k ? lo : 0u));
           if (lane == k) mine = wk;
         }
       } else {
-        constexpr int NT = (32 + BPSYM - 1) / BPSYM + 1;                      // symbols that can touch one word
-        const int i0 = (32 * lane) / BPSYM, skip = 32 * lane - i0 * BPSYM;    // lanes >= BPSYM gather garbage, never stored
+        constexpr int NT = (32 + BPT - 1) / BPT + 1;                          // codes that can touch one word
+        const int i0 = (32 * lane) / BPT, skip = 32 * lane - i0 * BPT;        // lanes >= BPT gather garbage, never stored
         unsigned long long acc = 0;
 #pragma unroll
-        for (int u = 0; u < NT; ++u) acc = (acc << BPSYM) | (unsigned long long)__shfl_sync(0xffffffffu, code, min(i0 + u, 31));
-        mine = (uint32_t)(acc >> (NT * BPSYM - 32 - skip));
+        for (int u = 0; u < NT; ++u) acc = (acc << BPT) | (unsigned long long)__shfl_sync(0xffffffffu, code, min(i0 + u, 31));
+        mine = (uint32_t)(acc >> (NT * BPT - 32 - skip));
       }
-      const int sw = s0 + (tid & ~31);                                        // first symbol of this warp's 32
-      if (lane < BPSYM && sw * BPSYM + 32 * lane < ns * BPSYM)
+      const int sw = (q0 + (tid & ~31)) * SPT;                                // first symbol of this warp's 32 * SPT
+      if (lane < BPT && sw * BPSYM + 32 * lane < ns * BPSYM)
         v1_store_word(a, d, (uint64_t)(d.k0 + sw) * BPSYM / 32 + lane, mine);
     }
     __syncwarp();
@@ -643,22 +658,24 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   if ((p.prefilter || dtype == FB_F32) && !getenv("FB_V1_GENERIC")) {
     const bool psk = p.mode <= V1_PSK8 && p.off0 == 0 && p.len == p.sps && nfu == 1;
     if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20)) sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : 6) + p.mode;
-    else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7) sym_id = 9;
+    else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7 && map[4] == 0x102 && map[5] == 0x101 &&
+             map[6] == 0x100) sym_id = 9;
     else if (p.mode == V1_OFDM && p.sps == 20 && p.off0 == 5 && p.len == 15 && nfu == 4 && p.nf == 4) sym_id = 10;
     else if (p.mode == V1_FSK && p.off0 == 0 && p.len == p.sps && nfu == 2 && (p.sps == 10 || p.sps == 5 || p.sps == 20))
       sym_id = p.sps == 10 ? 11 : p.sps == 5 ? 12 : 13;
   }
   if (sym_id >= 0) G = 1;
+  const int spt = (sym_id >= 3 && sym_id <= 5) ? 4 : 1;                      // symbols per thread (must match the launch table)
   size_t tile_target = 20480;
   int stages = 2;
   if (const char* e = getenv("FB_V1_TILE")) tile_target = (size_t)std::max(1024, atoi(e));      // tuning knobs
   if (const char* e = getenv("FB_V1_STAGES")) stages = std::max(2, std::min(V1_STAGES, atoi(e)));
   // whole passes of the 256 consumer threads (V1_THREADS / G symbols each), so no pass runs with idle warps
-  const int SP = std::max(32, V1_THREADS / G);
+  const int SP = std::max(32, V1_THREADS / G) * spt;
   int S = (int)std::min<size_t>(4096, (tile_target / ((size_t)p.sps * kesz)) / SP * SP);
   if (S < SP) S = (int)std::max<size_t>(32, std::min<size_t>(SP, (tile_target / ((size_t)p.sps * kesz)) / 32 * 32));
-  // +48: alignment skew of the bulk copy (<= 12) and the over-read of v1_sym_kernel's aligned vector loads
-  const size_t raw_bytes = ((size_t)S * p.sps * kesz + 48 + 127) / 128 * 128;
+  // +96: alignment skew of the bulk copy (<= 12) and the over-read of v1_sym_kernel's aligned vector loads
+  const size_t raw_bytes = ((size_t)S * p.sps * kesz + 96 + 127) / 128 * 128;
   const size_t smem = sym_id >= 0 ? stages * raw_bytes + 128 : stages * raw_bytes + (size_t)NFU * p.len * 16 + (size_t)S * 2 + 16;
   if (smem > 200 * 1024) return FB_EUNSUPPORTED;
   std::vector<RecPlan> plans(n_rec);
@@ -792,20 +809,20 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
         kern<<<grid, V1_THREADS + 32, smem, h->stream>>>(a, wt);                                                        \
       } break;
       switch (sym_id) {
-        FB_V1_SYM(0, V1_BPSK, 10, 0, 10, 1, 1)
-        FB_V1_SYM(1, V1_QPSK, 10, 0, 10, 1, 1)
-        FB_V1_SYM(2, V1_PSK8, 10, 0, 10, 1, 1)
-        FB_V1_SYM(3, V1_BPSK, 2, 0, 2, 1, 1)
-        FB_V1_SYM(4, V1_QPSK, 2, 0, 2, 1, 1)
-        FB_V1_SYM(5, V1_PSK8, 2, 0, 2, 1, 1)
-        FB_V1_SYM(6, V1_BPSK, 20, 0, 20, 1, 1)
-        FB_V1_SYM(7, V1_QPSK, 20, 0, 20, 1, 1)
-        FB_V1_SYM(8, V1_PSK8, 20, 0, 20, 1, 1)
-        FB_V1_SYM(9, V1_OFDM, 10, 2, 8, 4, 7)
-        FB_V1_SYM(10, V1_OFDM, 20, 5, 15, 4, 4)
-        FB_V1_SYM(11, V1_FSK, 10, 0, 10, 2, 1)
-        FB_V1_SYM(12, V1_FSK, 5, 0, 5, 2, 1)
-        FB_V1_SYM(13, V1_FSK, 20, 0, 20, 2, 1)
+        FB_V1_SYM(0, V1_BPSK, 10, 0, 10, 1, 1, 1)
+        FB_V1_SYM(1, V1_QPSK, 10, 0, 10, 1, 1, 1)
+        FB_V1_SYM(2, V1_PSK8, 10, 0, 10, 1, 1, 1)
+        FB_V1_SYM(3, V1_BPSK, 2, 0, 2, 1, 1, 4)
+        FB_V1_SYM(4, V1_QPSK, 2, 0, 2, 1, 1, 4)
+        FB_V1_SYM(5, V1_PSK8, 2, 0, 2, 1, 1, 4)
+        FB_V1_SYM(6, V1_BPSK, 20, 0, 20, 1, 1, 1)
+        FB_V1_SYM(7, V1_QPSK, 20, 0, 20, 1, 1, 1)
+        FB_V1_SYM(8, V1_PSK8, 20, 0, 20, 1, 1, 1)
+        FB_V1_SYM(9, V1_OFDM, 10, 2, 8, 4, 7, 1)
+        FB_V1_SYM(10, V1_OFDM, 20, 5, 15, 4, 4, 1)
+        FB_V1_SYM(11, V1_FSK, 10, 0, 10, 2, 1, 1)
+        FB_V1_SYM(12, V1_FSK, 5, 0, 5, 2, 1, 1)
+        FB_V1_SYM(13, V1_FSK, 20, 0, 20, 2, 1, 1)
         default: return FB_EINVAL;
       }
 #undef FB_V1_SYM
