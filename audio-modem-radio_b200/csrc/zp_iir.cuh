@@ -71,24 +71,21 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_fwd_kernel(const void* samples,
     const int64_t e_lo = cb * L + kb, e_hi = (cb + ZP_THREADS - 1) * L + kb + ZP_EB - 1;
     return kb < L && (e_lo - t.pad >= 0) && (e_hi - t.pad <= N - 1) && (e_lo > 0);
   };
-  auto load_inner = [&](int kb, double (&v)[ZP_EB]) {               // this thread's share of the cooperative load
+  // raw values: converting here would make the warp wait for the loads before the current block's math
+  auto load_inner = [&](int kb, TIn (&v)[ZP_EB]) {                  // this thread's share of the cooperative load
     const TIn* p = xin + (cb * L + kb + (int64_t)sg * L + su - t.pad);
     const int64_t stride = 4 * (int64_t)L;
 #pragma unroll
-    for (int i = 0; i < ZP_EB; ++i) {
-      if (sizeof(TIn) == 2) v[i] = (double)__ldg(reinterpret_cast<const int16_t*>(p)) * (1.0 / 32768.0);
-      else v[i] = (double)__ldg(p);
-      p += stride;
-    }
+    for (int i = 0; i < ZP_EB; ++i) { v[i] = __ldg(p); p += stride; }
   };
-  double pre[ZP_EB];                                                // next block's inputs, in flight during this block's math
+  TIn pre[ZP_EB];                                                   // next block's inputs, in flight during this block's math
   bool pre_ok = is_inner(-W16);
   if (pre_ok) load_inner(-W16, pre);
   for (int kb = -W16; kb < L; kb += ZP_EB) {
     const bool inner = pre_ok;
     if (inner) {
 #pragma unroll
-      for (int i = 0; i < ZP_EB; ++i) xs[sg + 4 * i][su] = pre[i];
+      for (int i = 0; i < ZP_EB; ++i) xs[sg + 4 * i][su] = sizeof(TIn) == 2 ? (double)pre[i] * (1.0 / 32768.0) : (double)pre[i];
     } else {
       for (int idx = tid; idx < ZP_THREADS * ZP_EB; idx += ZP_THREADS) {
         const int seg = idx >> 4, u = idx & 15;

@@ -20,7 +20,7 @@ SYMBOLS = [
     "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
     "fb_rs_out_bound", "fb_viterbi_out_bound", "fb_rs_decode_batch", "fb_viterbi_decode_batch", "fb_crc32_batch",
     "fb_parse_frames_batch", "fb_fsk_out_bound", "fb_fsk_demod_batch", "fb_v1_out_bound", "fb_v1_demod_batch",
-    "fb_ingest_resample",
+    "fb_ingest_resample", "fb_mod_out_samples", "fb_modulate_batch",
 ]
 
 
@@ -96,6 +96,10 @@ def load() -> ctypes.CDLL:
     lib.fb_v1_demod_batch.argtypes = [vp, vp, vp, c.c_int, vp, u64p, c.c_int, c.c_int, u8p, u64p, vp, vp]
     lib.fb_ingest_resample.restype = c.c_int
     lib.fb_ingest_resample.argtypes = [vp, vp, c.c_uint64, c.c_int, c.c_int, c.c_uint64, vp, c.c_int]
+    lib.fb_mod_out_samples.restype = c.c_uint64
+    lib.fb_mod_out_samples.argtypes = [vp, c.c_uint64]
+    lib.fb_modulate_batch.restype = c.c_int
+    lib.fb_modulate_batch.argtypes = [vp, vp, vp, vp, c.c_int, vp, u64p, vp, u64p, c.c_int]
     _lib = lib
     return lib
 

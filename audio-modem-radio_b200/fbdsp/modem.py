@@ -54,3 +54,42 @@ def ft8_demodulate(s, b, c, sr=96000):
 def psk31_demodulate(s, b, c, sr=96000):
     """modem.py:397."""
     return bpsk_demodulate(s, 31.25, c, sr)
+
+
+# ---- TX side (SURVEY 8f-4): same names / defaults as modem.py:28,138,270,344,351,371,379 -----------------------------
+def bpsk_modulate(data_bytes: bytes, baud=1200, carrier=3000.0, samp_rate=96000):
+    """DBPSK, modem.py:28-65 (preamble [1,0]*40; 1 -> phase += pi; 10 % linear edge ramps)."""
+    from . import modulate as _m
+    return _m.modulate_batch([data_bytes], *_m.psk_mod_params(_m.FB_MOD_DBPSK, baud, carrier, samp_rate))[0]
+
+
+def qpsk_modulate(data_bytes: bytes, baud=1200, carrier=3000.0, samp_rate=96000):
+    """DQPSK, modem.py:138-186 (preamble [0,0]*30+[1,1]*10; 00 -> 0, 01 -> +pi/2, 11 -> pi, 10 -> -pi/2)."""
+    from . import modulate as _m
+    return _m.modulate_batch([data_bytes], *_m.psk_mod_params(_m.FB_MOD_DQPSK, baud, carrier, samp_rate))[0]
+
+
+def fsk_modulate(data_bytes: bytes, baud=1200, mark_freq=1200.0, space_freq=2200.0, samp_rate=96000):
+    """CPFSK, modem.py:270-295 (preamble AA AA AA AA, phase carried across bits modulo 2 pi, x 0.9)."""
+    from . import modulate as _m
+    return _m.modulate_batch([data_bytes], *_m.fsk_mod_params(baud, mark_freq, space_freq, samp_rate))[0]
+
+
+def psk8_modulate(d, b=1200, c=3000.0, s=96000):
+    """modem.py:344."""
+    return qpsk_modulate(d, b, c, s)
+
+
+def fsk_high_speed_modulate(d, baud=19200, s=96000):
+    """modem.py:351-352."""
+    return fsk_modulate(d, baud, 8000, 16000, s)
+
+
+def ofdm_modulate_simple(d, baud, carrier, num_subcarriers, samp_rate=96000):
+    """modem.py:371-372."""
+    return qpsk_modulate(d, baud, carrier, samp_rate)
+
+
+def apsk16_modulate(d, b, c, s=96000):
+    """modem.py:379."""
+    return qpsk_modulate(d, b, c, s)

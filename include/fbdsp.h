@@ -182,6 +182,26 @@ int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw, const uin
 int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frames, int n_channels, int dtype, uint64_t n_out,
                        double* out, int flags);
 
+/* ---- batch modulators (TX side): replace bpsk_modulate (modem.py:28-65), qpsk_modulate (modem.py:138-186;
+ * also psk8_modulate / ofdm_modulate_simple / apsk16_modulate, modem.py:344,371,379) and fsk_modulate (modem.py:270-295;
+ * also fsk_high_speed_modulate, modem.py:351) for n_rec payloads in one call.  The host wrapper builds the sps-entry
+ * tables with the reference's own numpy expressions: PSK base[j] = 2 pi carrier t_j and env[j] (10 % linear ramps,
+ * modem.py:57-61,179-183); CPFSK base[j] = t_j, env = NULL.  Symbols per payload: DBPSK 80 + 8 n, DQPSK 40 + 4 n,
+ * CPFSK 8 (4 + n) (preambles included).  data: payload bytes back to back (CSR data_offsets, n_rec + 1; host, or device
+ * with FB_SAMPLES_ON_DEVICE); out: float32 samples, payload r at out_offsets[r] (slot >= fb_mod_out_samples; host, or
+ * device with FB_OUT_ON_DEVICE).  Phases are accumulated sequentially in float64 exactly as the reference does.       */
+enum { FB_MOD_DBPSK = 0, FB_MOD_DQPSK = 1, FB_MOD_CPFSK = 2 };
+typedef struct fb_mod_params {
+  int32_t kind, sps;                 /* FB_MOD_*; int(fs / baud) for PSK, int(round(fs * (1 / baud))) for CPFSK          */
+  double  inc[4];                    /* PSK: phase change per code 2 b0 + b1 (DBPSK: [0, pi]); CPFSK: [space, mark] phase
+                                        advance per bit, 2 pi f (spb / fs)                                            */
+  double  wfreq[2];                  /* CPFSK: 2 pi f for [space, mark]                                               */
+  float   gain, pad;                 /* CPFSK: 0.9f (float32 multiply, modem.py:295)                                  */
+} fb_mod_params;
+uint64_t fb_mod_out_samples(const fb_mod_params* p, uint64_t n_bytes);
+int fb_modulate_batch(fb_handle* h, const fb_mod_params* p, const double* base, const double* env, int n_rec,
+                      const uint8_t* data, const uint64_t* data_offsets, float* out, const uint64_t* out_offsets, int flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,3 +138,106 @@ def test_v1_uart_deframer_dense(engine):
     st = v1.fsk_stages(x, 9600)
     assert g.fsk_demodulate(x, 9600) == st["raw"] == _uart_gold(st["bits"])
     assert len(st["raw"]) > 3000                                   # mostly framed bytes: long i += 10 runs
+
+
+def _sym_cases():
+    from fbdsp import modem_v1 as g
+    return {
+        "bpsk9600": lambda: g.psk_params(g.V1_BPSK, 9600, 3000.0), "qpsk9600": lambda: g.psk_params(g.V1_QPSK, 9600, 9600.0),
+        "psk8_9600": lambda: g.psk_params(g.V1_PSK8, 9600, 12000.0), "bpsk38400": lambda: g.psk_params(g.V1_BPSK, 38400, 12000.0),
+        "qpsk38400": lambda: g.psk_params(g.V1_QPSK, 38400, 12000.0), "psk8_38400": lambda: g.psk_params(g.V1_PSK8, 38400, 12000.0),
+        "bpsk4800": lambda: g.psk_params(g.V1_BPSK, 4800, 3000.0), "qpsk4800": lambda: g.psk_params(g.V1_QPSK, 4800, 9600.0),
+        "psk8_4800": lambda: g.psk_params(g.V1_PSK8, 4800, 12000.0), "ofdm8_9600": lambda: g.ofdm_params(9600, 8),
+        "ofdm4_4800": lambda: g.ofdm_params(4800, 4), "fsk9600": lambda: g.fsk_params(9600, 8000.0, 16000.0, 7500, 16500, True),
+        "fskhs19200": lambda: g.fsk_params(19200, 12000.0, 18000.0, 8000, 22000, False),
+        "fsk4800": lambda: g.fsk_params(4800, 8000.0, 16000.0, 7500, 16500, True),
+    }
+
+
+@pytest.mark.parametrize("name", ["bpsk9600", "qpsk9600", "psk8_9600", "bpsk38400", "qpsk38400", "psk8_38400", "bpsk4800", "qpsk4800",
+                                  "psk8_4800", "ofdm8_9600", "ofdm4_4800", "fsk9600", "fskhs19200", "fsk4800"])
+def test_v1_sym_kernel_equals_generic(name, engine, monkeypatch):
+    """Every compile-time geometry of v1_sym_kernel against the generic v1_corr_kernel (itself checked against the
+    restatement above) on a ragged batch whose recordings start at every residue mod 4 (all register-shift phases of
+    the vector symbol loads), span several tiles, end inside a tile, or hold less than one symbol: byte-exact -- both
+    kernels evaluate the same FMA chains."""
+    from fbdsp import modem_v1 as g
+    p, table = _sym_cases()[name]()
+    rng = np.random.default_rng(len(name) * 1000 + p.sps)
+    lens = [30001, 30, 40002, 1, 61443, 8191, 29, 123457, 31, 50000]
+    recs = [(rng.standard_normal(n) * 0.4).astype(np.float32) for n in lens]
+    monkeypatch.delenv("FB_V1_GENERIC", raising=False)
+    fast = g.demod_batch(recs, p, table, engine)
+    monkeypatch.setenv("FB_V1_GENERIC", "1")
+    slow = g.demod_batch(recs, p, table, engine)
+    assert [s for _, s in fast] == [s for _, s in slow]
+    for (a, _), (b, _), n in zip(fast, slow, lens):
+        assert a == b, f"{name}: recording of {n} samples differs"
+    assert sum(len(a) for a, _ in fast) > 1000
+
+
+def test_v1_sym_kernel_oracle_multi(engine):
+    """The specialised kernels directly against the restatement on a ragged batch (QPSK-9600, 8PSK-38400, OFDM8)."""
+    from fbdsp import modem_v1 as g
+    rng = np.random.default_rng(99)
+    lens = [20001, 3, 40962, 12345, 77777]
+    for mode, baud, carrier, bps, stages in ((g.V1_QPSK, 9600, 9600.0, 2, v1.qpsk_stages), (g.V1_PSK8, 38400, 12000.0, 3, v1.psk8_stages)):
+        recs = [_psk_signal(bps, baud, carrier, max(1, n // int(round(96000 / baud))), 12, n) for n in lens]
+        out = g.demod_batch(recs, *g.psk_params(mode, baud, carrier), engine)
+        for x, (raw, _) in zip(recs, out):
+            st = stages(x, baud, carrier)
+            if mode == g.V1_QPSK:
+                mag = np.hypot(st["i"], st["q"])
+                margin = np.minimum(np.abs(st["i"]), np.abs(st["q"])) / np.where(mag > 0, mag, 1)
+            else:
+                thr = np.array([1, 3, 5, 7, 9, 11, 13, 16]) * np.pi / 8
+                margin = np.min(np.abs(st["phi"][:, None] - thr[None, :]), axis=1) / (np.pi / 8)
+            _check(raw, st, margin, bps)
+    recs = [rng.standard_normal(n).astype(np.float32) for n in lens]
+    out = g.demod_batch(recs, *g.ofdm_params(9600, 8), engine)
+    for x, (raw, _) in zip(recs, out):
+        st = v1.ofdm_stages(x, 9600, 12000.0, 8)
+        sc = st["sc"].reshape(-1)
+        margin = np.minimum(np.abs(sc.real), np.abs(sc.imag)) / np.maximum(np.abs(sc), 1e-300)
+        _check(raw, st, margin, 2)
+
+
+def test_v1_sym_kernel_specials(engine):
+    """Digital silence, exact sector centres / edges and non-finite samples through the sign-bit slicers."""
+    from fbdsp import modem_v1 as g
+    z = np.zeros(4000, np.float32)
+    for mode, baud, carrier, f in ((g.V1_QPSK, 9600, 9600.0, v1.qpsk_demodulate), (g.V1_BPSK, 9600, 3000.0, v1.bpsk_demodulate),
+                                   (g.V1_PSK8, 38400, 12000.0, v1.psk8_demodulate), (g.V1_PSK8, 9600, 12000.0, v1.psk8_demodulate)):
+        raw, _ = g.demod_batch([z], *g.psk_params(mode, baud, carrier), engine)[0]
+        assert raw == f(z, baud, carrier)
+    raw, _ = g.demod_batch([z], *g.ofdm_params(9600, 8), engine)[0]
+    assert raw == v1.ofdm_demodulate_simple(z, 9600, 12000.0, 8)
+    # noiseless 8PSK steered (2x2 solve for the non-orthogonal 1.25-cycle references) to sector centres, to 3e-5 rad either
+    # side of every edge (must match exactly) and onto the edges themselves (a 1-ulp atan2 difference may flip those:
+    # margin rule only)
+    sps = 10
+    t = np.arange(sps) / 96000
+    rc, rs = np.cos(2 * np.pi * 12000.0 * t), np.sin(2 * np.pi * 12000.0 * t)
+    gram = np.array([[rc @ rc, rc @ rs], [rc @ rs, rs @ rs]])
+    edges = np.arange(1, 16, 2) * np.pi / 8
+    for delta, exact in ((3e-5, True), (-3e-5, True), (0.0, False)):
+        th = np.concatenate([edges + delta, np.arange(8) * np.pi / 4])
+        ab = np.linalg.solve(gram, np.stack([np.cos(th), np.sin(th)]))
+        x = (ab[0][:, None] * rc[None, :] + ab[1][:, None] * rs[None, :]).reshape(-1)
+        x = np.tile(x, 24).astype(np.float32)
+        raw, _ = g.demod_batch([x], *g.psk_params(g.V1_PSK8, 9600, 12000.0), engine)[0]
+        st = v1.psk8_stages(x, 9600, 12000.0)
+        thr = np.array([1, 3, 5, 7, 9, 11, 13, 16]) * np.pi / 8
+        margin = np.min(np.abs(st["phi"][:, None] - thr[None, :]), axis=1) / (np.pi / 8)
+        if exact:
+            assert margin.min() > 1e-5 and raw == st["raw"]
+        else:
+            want, got = st["bits"][: len(st["bits"]) // 8 * 8], _bits(raw)
+            assert len(want) == len(got)
+            for b_ in np.nonzero(want != got)[0]:
+                assert margin[b_ // 3] < 1e-5
+    # NaN samples: the QPSK comparison chain of B.5 falls through to '10'
+    y = (np.random.default_rng(3).standard_normal(4000) * 0.3).astype(np.float32)
+    y[105] = np.nan
+    raw, _ = g.demod_batch([y], *g.psk_params(g.V1_QPSK, 9600, 9600.0), engine)[0]
+    assert raw == v1.qpsk_demodulate(y, 9600, 9600.0)
