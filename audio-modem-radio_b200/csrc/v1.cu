@@ -367,7 +367,7 @@ __device__ __forceinline__ uint32_t psk8_code_folded(double I, double Q) {
 // Non-finite samples: a NaN accumulator decides '10' per (I, Q) pair like the comparison chain of B.5 does; OFDM tests
 // the first bin only (scipy's FFT and a direct DFT spread an Inf differently anyway).
 template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF, int SPT>
-__global__ void __launch_bounds__(V1_THREADS + 32, 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
+__global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 40 ? 2 : 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
   constexpr int BPSYM = MODE == V1_BPSK ? 1 : MODE == V1_QPSK ? 2 : MODE == V1_PSK8 ? 3 : MODE == V1_OFDM ? 2 * NF : 1;
   constexpr int BPT = BPSYM * SPT;                                            // bits per thread and pass
   constexpr int STRIDE = SPS * SPT;                                           // samples between consecutive threads
@@ -657,7 +657,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   int sym_id = -1;
   if ((p.prefilter || dtype == FB_F32) && !getenv("FB_V1_GENERIC")) {
     const bool psk = p.mode <= V1_PSK8 && p.off0 == 0 && p.len == p.sps && nfu == 1;
-    if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20)) sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : 6) + p.mode;
+    if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20 || p.sps == 40)) sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : p.sps == 20 ? 6 : 14) + p.mode;
     else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7 && map[4] == 0x102 && map[5] == 0x101 &&
              map[6] == 0x100) sym_id = 9;
     else if (p.mode == V1_OFDM && p.sps == 20 && p.off0 == 5 && p.len == 15 && nfu == 4 && p.nf == 4) sym_id = 10;
@@ -667,6 +667,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   if (sym_id >= 0) G = 1;
   const int spt = (sym_id >= 3 && sym_id <= 5) ? 4 : 1;                      // symbols per thread (must match the launch table)
   size_t tile_target = 20480;
+  if (sym_id >= 0) tile_target = std::max<size_t>(tile_target, (size_t)V1_THREADS * p.sps * 4);   // at least one full pass per tile
   int stages = 2;
   if (const char* e = getenv("FB_V1_TILE")) tile_target = (size_t)std::max(1024, atoi(e));      // tuning knobs
   if (const char* e = getenv("FB_V1_STAGES")) stages = std::max(2, std::min(V1_STAGES, atoi(e)));
@@ -823,6 +824,9 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
         FB_V1_SYM(11, V1_FSK, 10, 0, 10, 2, 1, 1)
         FB_V1_SYM(12, V1_FSK, 5, 0, 5, 2, 1, 1)
         FB_V1_SYM(13, V1_FSK, 20, 0, 20, 2, 1, 1)
+        FB_V1_SYM(14, V1_BPSK, 40, 0, 40, 1, 1, 1)
+        FB_V1_SYM(15, V1_QPSK, 40, 0, 40, 1, 1, 1)
+        FB_V1_SYM(16, V1_PSK8, 40, 0, 40, 1, 1, 1)
         default: return FB_EINVAL;
       }
 #undef FB_V1_SYM

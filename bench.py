@@ -199,7 +199,8 @@ def scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets, steps=3):
 
     for name, (p, table) in {"v1_qpsk_9600": g.psk_params(g.V1_QPSK, 9600, 9600.0), "v1_bpsk_9600": g.psk_params(g.V1_BPSK, 9600, 3000.0),
                              "v1_ofdm8_9600": g.ofdm_params(9600, 8), "v1_ofdm4_4800": g.ofdm_params(4800, 4),
-                             "v1_psk8_2400": g.psk_params(g.V1_PSK8, 2400, 12000.0)}.items():
+                             "v1_psk8_2400": g.psk_params(g.V1_PSK8, 2400, 12000.0),
+                             "v1_psk8_38400": g.psk_params(g.V1_PSK8, 38400, 12000.0)}.items():
         size = (int(eng.lib.fb_v1_out_bound(ctypes.byref(p), n_samp)) + 7) // 4 * 4
         oo = np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(size)
         buf = torch.empty(n_rec * size + 16, dtype=torch.uint8, device=dev)
