@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 //     uniform over a tile (sps % VEC == 0), so the register shift is a warp-uniform switch
 //   * 32 symbols of a warp are always BPSYM whole words: redux.sync OR for BPSYM <= 4, a shuffle gather for wider codes
 //     (OFDM8's 14 bits, 8PSK's 3) -- no shared-memory code table and no CTA barrier for any mode
-struct V1Weights { double2 w[64]; };          // [j * NFU + m], unique rows only
+struct V1Weights { double2 w[80]; };          // [j * NFU + m], unique rows only
 
 __device__ __noinline__ uint32_t psk8_code_slow(double I, double Q) { return psk8_code(I, Q); }   // rare: keep it out of line
 
@@ -367,14 +367,14 @@ __device__ __forceinline__ uint32_t psk8_code_folded(double I, double Q) {
 // Non-finite samples: a NaN accumulator decides '10' per (I, Q) pair like the comparison chain of B.5 does; OFDM tests
 // the first bin only (scipy's FFT and a direct DFT spread an Inf differently anyway).
 template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF, int SPT>
-__global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 40 ? 2 : 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
+__global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2 : 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
   constexpr int BPSYM = MODE == V1_BPSK ? 1 : MODE == V1_QPSK ? 2 : MODE == V1_PSK8 ? 3 : MODE == V1_OFDM ? 2 * NF : 1;
   constexpr int BPT = BPSYM * SPT;                                            // bits per thread and pass
   constexpr int STRIDE = SPS * SPT;                                           // samples between consecutive threads
   constexpr int SPAN = (SPT - 1) * SPS + LEN;                                 // samples a thread correlates
   constexpr int VEC = (STRIDE % 4 == 0) ? 4 : (STRIDE % 2 == 0) ? 2 : 1;
   constexpr int NV = (SPAN + 2 * (VEC - 1)) / VEC;                            // aligned vectors that cover any phase
-  static_assert(NFU * LEN <= 64, "weights exceed the parameter table");
+  static_assert(NFU * LEN <= 80, "weights exceed the parameter table");
   static_assert(BPT <= 16, "code of one thread must fit the shuffle gather");
   extern __shared__ __align__(128) unsigned char v1_smem[];
   __shared__ __align__(8) unsigned long long full[V1_STAGES], empty[V1_STAGES];
@@ -657,7 +657,8 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
   int sym_id = -1;
   if ((p.prefilter || dtype == FB_F32) && !getenv("FB_V1_GENERIC")) {
     const bool psk = p.mode <= V1_PSK8 && p.off0 == 0 && p.len == p.sps && nfu == 1;
-    if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20 || p.sps == 40)) sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : p.sps == 20 ? 6 : 14) + p.mode;
+    if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20 || p.sps == 40 || p.sps == 80))
+      sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : p.sps == 20 ? 6 : p.sps == 40 ? 14 : 17) + p.mode;
     else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7 && map[4] == 0x102 && map[5] == 0x101 &&
              map[6] == 0x100) sym_id = 9;
     else if (p.mode == V1_OFDM && p.sps == 20 && p.off0 == 5 && p.len == 15 && nfu == 4 && p.nf == 4) sym_id = 10;
@@ -827,6 +828,9 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
         FB_V1_SYM(14, V1_BPSK, 40, 0, 40, 1, 1, 1)
         FB_V1_SYM(15, V1_QPSK, 40, 0, 40, 1, 1, 1)
         FB_V1_SYM(16, V1_PSK8, 40, 0, 40, 1, 1, 1)
+        FB_V1_SYM(17, V1_BPSK, 80, 0, 80, 1, 1, 1)
+        FB_V1_SYM(18, V1_QPSK, 80, 0, 80, 1, 1, 1)
+        FB_V1_SYM(19, V1_PSK8, 80, 0, 80, 1, 1, 1)
         default: return FB_EINVAL;
       }
 #undef FB_V1_SYM

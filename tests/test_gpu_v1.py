@@ -153,11 +153,13 @@ def _sym_cases():
         "fsk4800": lambda: g.fsk_params(4800, 8000.0, 16000.0, 7500, 16500, True),
         "bpsk2400": lambda: g.psk_params(g.V1_BPSK, 2400, 3000.0), "qpsk2400": lambda: g.psk_params(g.V1_QPSK, 2400, 3000.0),
         "psk8_2400": lambda: g.psk_params(g.V1_PSK8, 2400, 12000.0),
+        "bpsk1200": lambda: g.psk_params(g.V1_BPSK, 1200, 3000.0), "qpsk1200": lambda: g.psk_params(g.V1_QPSK, 1200, 3000.0),
+        "psk8_1200": lambda: g.psk_params(g.V1_PSK8, 1200, 12000.0),
     }
 
 
 @pytest.mark.parametrize("name", ["bpsk9600", "qpsk9600", "psk8_9600", "bpsk38400", "qpsk38400", "psk8_38400", "bpsk4800", "qpsk4800",
-                                  "psk8_4800", "ofdm8_9600", "ofdm4_4800", "fsk9600", "fskhs19200", "fsk4800", "bpsk2400", "qpsk2400", "psk8_2400"])
+                                  "psk8_4800", "ofdm8_9600", "ofdm4_4800", "fsk9600", "fskhs19200", "fsk4800", "bpsk2400", "qpsk2400", "psk8_2400", "bpsk1200", "qpsk1200", "psk8_1200"])
 def test_v1_sym_kernel_equals_generic(name, engine, monkeypatch):
     """Every compile-time geometry of v1_sym_kernel against the generic v1_corr_kernel (itself checked against the
     restatement above) on a ragged batch whose recordings start at every residue mod 4 (all register-shift phases of
@@ -175,7 +177,7 @@ def test_v1_sym_kernel_equals_generic(name, engine, monkeypatch):
     assert [s for _, s in fast] == [s for _, s in slow]
     for (a, _), (b, _), n in zip(fast, slow, lens):
         assert a == b, f"{name}: recording of {n} samples differs"
-    assert sum(len(a) for a, _ in fast) > 500
+    assert sum(len(a) for a, _ in fast) > 300
 
 
 def test_v1_sym_kernel_oracle_multi(engine):
