@@ -124,6 +124,29 @@ __device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2);
 
 // SPS > 0: samples per symbol (and, with PP > 0, the shared-memory row pitch) known at compile time (even): the staging loop is fully unrolled with all
 // of a thread's loads in flight before the first store; SPS == 0: runtime sps.
+#ifdef PM_TRACE
+// Phase timeline of the main kernel (experiments only; build with NVCC_EXTRA=-DPM_TRACE into a separate .so):
+// thread 0 of the first PM_TRACE_N CTAs records %globaltimer at the phase boundaries and its SM id.
+#define PM_TRACE_N 16384
+__device__ unsigned long long pm_trace_t[PM_TRACE_N][8];
+__device__ unsigned int pm_trace_sm[PM_TRACE_N];
+__device__ __forceinline__ void pm_mark(int k) {
+  if (threadIdx.x == 0 && blockIdx.x < PM_TRACE_N) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    pm_trace_t[blockIdx.x][k] = t;
+    if (k == 0) { unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); pm_trace_sm[blockIdx.x] = sm; }
+  }
+}
+extern "C" int fb_debug_pm_trace(unsigned long long* t, unsigned int* sm) {
+  if (cudaMemcpyFromSymbol(t, pm_trace_t, sizeof(pm_trace_t)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(sm, pm_trace_sm, sizeof(pm_trace_sm)) != cudaSuccess) return -1;
+  return PM_TRACE_N;
+}
+#else
+__device__ __forceinline__ void pm_mark(int) {}
+#endif
+
 template <typename TIn, int NT, int SPS, int PP>
 __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -132,9 +155,12 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   __shared__ float2 s_car[8][4];         // state entering each warp [warp][seq]
   __shared__ float2 s_y0[9];             // y of each warp's first symbol (differential across warp edges)
   __shared__ double finit_sh[2 * FB_MAX_SLOW];
+  __shared__ float2 s_tbl[FB_MAX_SLOW * SLOW_TBL];   // scan multipliers (a.slow_tbl): read at LDS latency inside the dependent scan chain
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
   const int sps = SPS ? SPS : a.sps;
   constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
+  pm_mark(0);
+  for (int i = threadIdx.x; i < a.nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
   // ---- this CTA's tile ---------------------------------------------------------------------------------------
   const uint32_t tile = blockIdx.x;
   const PskTile pl = a.tiles[tile];
@@ -208,6 +234,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       }
     }
   }
+  pm_mark(1);
   // ---- L2 prefetch for the CTA that will run about one tile-time from now (same SM slot, pf_dist tiles ahead): its
   // staging and boundary loads then hit L2 instead of paying the DRAM latency
   if (tile + a.pf_dist < a.n_tiles) {
@@ -284,7 +311,9 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       if (lane == 0) { s_bnd[pair >> 1][fwd ? 0 : 1][slice][0] = bs0; s_bnd[pair >> 1][fwd ? 0 : 1][slice][1] = bs1; }
     }
   }
+  pm_mark(2);
   __syncthreads();                                  // staged samples, finit and the boundary sums are visible
+  pm_mark(3);
 
   // this thread's PM_CH symbols e0 .. e0+7 (global d0 + e); y accumulates the slow part, then the FIR
   const int e0 = tid * PM_CH;
@@ -356,8 +385,8 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       }
     }
     // (3) thread totals -> warp scan (shuffle up: forward, shuffle down: backward) -> serial carry over warps
-    const float2* tb0 = a.slow_tbl + (size_t)pair * SLOW_TBL;
-    const float2* tb1 = a.slow_tbl + (size_t)i1 * SLOW_TBL;
+    const float2* tb0 = s_tbl + pair * SLOW_TBL;
+    const float2* tb1 = s_tbl + i1 * SLOW_TBL;
     float2 v[4];
     {
       float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
@@ -372,7 +401,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     }
 #pragma unroll
     for (int st = 0; st < 5; ++st) {
-      const float2 m0 = __ldg(&tb0[32 + st]), m1 = __ldg(&tb1[32 + st]);   // m^(2^st), m = lam^PM_CH
+      const float2 m0 = tb0[32 + st], m1 = tb1[32 + st];   // m^(2^st), m = lam^PM_CH
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 mm = (k & 1) ? m1 : m0;
@@ -391,7 +420,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     if (tid < 4) {
       const int k = tid;
       const float2* tb = (k & 1) ? tb1 : tb0;
-      const float2 M = __ldg(&tb[38]);                // m^32
+      const float2 M = tb[38];                // m^32
       if (k < 2) {                                    // state entering warp w from the left; warp 0: Fst[d0]
         float2 c = make_float2(s_bnd[pair >> 1][0][0][k].x + s_bnd[pair >> 1][0][1][k].x + s_bnd[pair >> 1][0][2][k].x + s_bnd[pair >> 1][0][3][k].x,
                                s_bnd[pair >> 1][0][0][k].y + s_bnd[pair >> 1][0][1][k].y + s_bnd[pair >> 1][0][2][k].y + s_bnd[pair >> 1][0][3][k].y);
@@ -420,7 +449,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
         else { ex = __shfl_down_sync(0xffffffffu, v[k].x, 1); ey = __shfl_down_sync(0xffffffffu, v[k].y, 1); }
         const bool has = (k < 2) ? lane > 0 : lane < 31;
         const float2 excl = has ? make_float2(ex, ey) : make_float2(0.f, 0.f);
-        sc[k] = cfma2(__ldg(&tb[(k < 2) ? lane : 31 - lane]), s_car[warp][k], excl);
+        sc[k] = cfma2(tb[(k < 2) ? lane : 31 - lane], s_car[warp][k], excl);
       }
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 af0 = a.af[pair], af1 = two ? a.af[i1] : z4, ab0 = a.ab[pair], ab1 = two ? a.ab[i1] : z4;
@@ -445,6 +474,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     if (pair + 2 < a.nslow) __syncthreads();          // s_tot / s_car are rewritten by the next pair
   }
 
+  pm_mark(4);
   // ---- fast part: register-tiled polyphase FIR at symbol instants --------------------------------
   //   y[s] += tapsR[j][t'] * X[j][e0 + PADL + s + t']   -- one FFMA2 per (complex tap, real sample), taps as uniform operands
   if (active) {
@@ -497,6 +527,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     }
   }
 
+  pm_mark(5);
   // ---- differential decisions: PM_CH per thread, 32-bit big-endian words assembled across 2 (DQPSK) / 4 (DBPSK) lanes --
   {
     if (lane == 0) s_y0[warp] = y[0];
@@ -536,6 +567,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       if ((lane & 3) == 0 && e0 < nd) a.bits[pl.word_off + (uint64_t)((d0 + e0) >> 5)] = __byte_perm(wv, 0, 0x0123);
     }
   }
+  pm_mark(6);
 }
 
 // =====================================================================================================
