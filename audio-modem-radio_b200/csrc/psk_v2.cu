@@ -128,7 +128,7 @@ __device__ __forceinline__ int pm_swz(int c) { return c ^ (((c >> 5) & 1) << 2);
 // Phase timeline of the main kernel (experiments only; build with NVCC_EXTRA=-DPM_TRACE into a separate .so):
 // thread 0 of the first PM_TRACE_N CTAs records %globaltimer at the phase boundaries and its SM id.
 #define PM_TRACE_N 16384
-__device__ unsigned long long pm_trace_t[PM_TRACE_N][8];
+__device__ unsigned long long pm_trace_t[PM_TRACE_N][12];
 __device__ unsigned int pm_trace_sm[PM_TRACE_N];
 __device__ __forceinline__ void pm_mark(int k) {
   if (threadIdx.x == 0 && blockIdx.x < PM_TRACE_N) {
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
         }
       }
     }
+    pm_mark(7);
     // (3) thread totals -> warp scan (shuffle up: forward, shuffle down: backward) -> serial carry over warps
     const float2* tb0 = s_tbl + pair * SLOW_TBL;
     const float2* tb1 = s_tbl + i1 * SLOW_TBL;
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
         }
       }
     }
+    pm_mark(8);
     if (lane == 31) { s_tot[warp][0] = v[0]; s_tot[warp][1] = v[1]; }
     if (lane == 0) { s_tot[warp][2] = v[2]; s_tot[warp][3] = v[3]; }
     __syncthreads();
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       }
     }
     __syncthreads();
+    pm_mark(9);
     // (4) states entering this thread's chunk, then the per-column recursion and the residue maps
     {
       float2 sc[4];

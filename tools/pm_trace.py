@@ -23,7 +23,7 @@ for _ in range(3):
     eng.psk_demod_raw(d, batch.data_ptr(), offsets, _lib.FB_F32, flags, out.data_ptr(), oo, ol.data_ptr(), sy.data_ptr(), st.data_ptr())
 eng.sync()
 N = 16384
-t = np.zeros((N, 8), dtype=np.uint64); sm = np.zeros(N, dtype=np.uint32)
+t = np.zeros((N, 12), dtype=np.uint64); sm = np.zeros(N, dtype=np.uint32)
 got = eng.lib.fb_debug_pm_trace(t.ctypes.data, sm.ctypes.data)
 assert got == N, got
 n_tiles = min(N, n_rec * (n // 10 // 2016))
@@ -33,6 +33,11 @@ res = {names[i]: round(float(np.median(t[:, i + 1] - t[:, i])) / 1e3, 2) for i i
 res["residency_us"] = round(float(np.median(t[:, 6] - t[:, 0])) / 1e3, 2)
 res["p90_residency_us"] = round(float(np.percentile(t[:, 6] - t[:, 0], 90)) / 1e3, 2)
 span = (t[:, 6].max() - t[:, 0].min()) / 1e3
+if t[:, 7].min() > 0:                                     # finer marks inside the slow-pole phase
+    res["slow: features"] = round(float(np.median(t[:, 7] - t[:, 3])) / 1e3, 2)
+    res["slow: fold + warp scan"] = round(float(np.median(t[:, 8] - t[:, 7])) / 1e3, 2)
+    res["slow: carry (2 barriers)"] = round(float(np.median(t[:, 9] - t[:, 8])) / 1e3, 2)
+    res["slow: column recursion"] = round(float(np.median(t[:, 4] - t[:, 9])) / 1e3, 2)
 res["tiles"] = int(len(t)); res["span_us"] = round(float(span), 1)
 res["tiles_per_sm_slot_us"] = round(float(span) * 148 * 2 / len(t), 2)
 print(json.dumps(res))
