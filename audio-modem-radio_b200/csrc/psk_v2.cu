@@ -152,7 +152,6 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   extern __shared__ __align__(16) float smem[];
   __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
   __shared__ float2 s_tot[8][4];         // warp totals of the column scan [warp][seq]
-  __shared__ float2 s_car[8][4];         // state entering each warp [warp][seq]
   __shared__ float2 s_y0[9];             // y of each warp's first symbol (differential across warp edges)
   __shared__ double finit_sh[2 * FB_MAX_SLOW];
   __shared__ float2 s_tbl[FB_MAX_SLOW * SLOW_TBL];   // scan multipliers (a.slow_tbl): read at LDS latency inside the dependent scan chain
@@ -419,27 +418,32 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     if (lane == 31) { s_tot[warp][0] = v[0]; s_tot[warp][1] = v[1]; }
     if (lane == 0) { s_tot[warp][2] = v[2]; s_tot[warp][3] = v[3]; }
     __syncthreads();
-    if (tid < 4) {
-      const int k = tid;
+    // state entering this warp: lanes 0-3 (k = lane) fold the totals of the warps before (forward) / after (backward) it,
+    // every warp for itself -- no serial section behind a second CTA barrier
+    float2 car[4];
+    {
+      const int k = lane & 3;
       const float2* tb = (k & 1) ? tb1 : tb0;
-      const float2 M = tb[38];                // m^32
-      if (k < 2) {                                    // state entering warp w from the left; warp 0: Fst[d0]
-        float2 c = make_float2(s_bnd[pair >> 1][0][0][k].x + s_bnd[pair >> 1][0][1][k].x + s_bnd[pair >> 1][0][2][k].x + s_bnd[pair >> 1][0][3][k].x,
-                               s_bnd[pair >> 1][0][0][k].y + s_bnd[pair >> 1][0][1][k].y + s_bnd[pair >> 1][0][2][k].y + s_bnd[pair >> 1][0][3][k].y);
-        if (near_left) {                              // + p^(n_d0 - n0) Fst[0]
-          const int i = (k == 0) ? pair : i1;
-          const float4 pw4 = __ldg(&a.slow_pw4[(size_t)(pair >> 1) * a.wpad + (int)(n_d0 - a.n0)]);
-          const float2 pw = (k == 0) ? make_float2(pw4.x, pw4.y) : make_float2(pw4.z, pw4.w);
-          (void)i;
-          c = cfma2(pw, make_float2((float)finit_sh[2 * i], (float)finit_sh[2 * i + 1]), c);
+      const float2 M = tb[38];                        // m^32
+      float2 c = make_float2(0.f, 0.f);
+      if (lane < 4) {
+        if (k < 2) {                                  // from the left; warp 0: Fst[d0]
+          c = make_float2(s_bnd[pair >> 1][0][0][k].x + s_bnd[pair >> 1][0][1][k].x + s_bnd[pair >> 1][0][2][k].x + s_bnd[pair >> 1][0][3][k].x,
+                          s_bnd[pair >> 1][0][0][k].y + s_bnd[pair >> 1][0][1][k].y + s_bnd[pair >> 1][0][2][k].y + s_bnd[pair >> 1][0][3][k].y);
+          if (near_left) {                            // + p^(n_d0 - n0) Fst[0]
+            const int i = (k == 0) ? pair : i1;
+            const float4 pw4 = __ldg(&a.slow_pw4[(size_t)(pair >> 1) * a.wpad + (int)(n_d0 - a.n0)]);
+            const float2 pw = (k == 0) ? make_float2(pw4.x, pw4.y) : make_float2(pw4.z, pw4.w);
+            c = cfma2(pw, make_float2((float)finit_sh[2 * i], (float)finit_sh[2 * i + 1]), c);
+          }
+          for (int w = 0; w < warp; ++w) c = cfma2(M, c, s_tot[w][k]);
+        } else {                                      // from the right (boundary already injected)
+          for (int w = nwarp - 1; w > warp; --w) c = cfma2(M, c, s_tot[w][k]);
         }
-        for (int w = 0; w < nwarp; ++w) { s_car[w][k] = c; c = cfma2(M, c, s_tot[w][k]); }
-      } else {                                        // state entering warp w from the right (boundary already injected)
-        float2 c = make_float2(0.f, 0.f);
-        for (int w = nwarp - 1; w >= 0; --w) { s_car[w][k] = c; c = cfma2(M, c, s_tot[w][k]); }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) car[q] = make_float2(__shfl_sync(0xffffffffu, c.x, q), __shfl_sync(0xffffffffu, c.y, q));
     }
-    __syncthreads();
     pm_mark(9);
     // (4) states entering this thread's chunk, then the per-column recursion and the residue maps
     {
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
         else { ex = __shfl_down_sync(0xffffffffu, v[k].x, 1); ey = __shfl_down_sync(0xffffffffu, v[k].y, 1); }
         const bool has = (k < 2) ? lane > 0 : lane < 31;
         const float2 excl = has ? make_float2(ex, ey) : make_float2(0.f, 0.f);
-        sc[k] = cfma2(tb[(k < 2) ? lane : 31 - lane], s_car[warp][k], excl);
+        sc[k] = cfma2(tb[(k < 2) ? lane : 31 - lane], car[k], excl);
       }
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 af0 = a.af[pair], af1 = two ? a.af[i1] : z4, ab0 = a.ab[pair], ab1 = two ? a.ab[i1] : z4;
