@@ -59,6 +59,11 @@ struct PskMainArgs {
   const void* samples;
   const PskTile* tiles;         // one descriptor per CTA
   uint32_t n_tiles, pf_dist;    // pf_dist: the tile this many CTAs ahead gets its samples prefetched into L2
+  // uniform batch (equal-length recordings back to back, e.g. the parts of one file): the descriptor is arithmetic on
+  // these parameters -- no dependent global load at the top of the CTA.  uni_tpr == 0: read tiles[tile].
+  uint32_t uni_tpr;             // tiles per recording
+  int32_t uni_dl, uni_dr;       // dl32, dr32 of every recording
+  uint64_t uni_off0, uni_n, uni_wstride;
   const float4* slow_pw4;       // [pairs][wpad]  {p_a^k, p_b^k}, zero for k > wlen: weights of the tile-boundary state sums (global)
   int wpad;                     // entries per pole pair in slow_pw4 (>= wlen + 1 + 1024, so over-reads hit zeros)
   const float2* slow_tbl;       // [nslow][SLOW_TBL]  powers of m = lam^PM_CH used by the column scan (global)
@@ -162,7 +167,14 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   for (int i = threadIdx.x; i < a.nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
   // ---- this CTA's tile ---------------------------------------------------------------------------------------
   const uint32_t tile = blockIdx.x;
-  const PskTile pl = a.tiles[tile];
+  PskTile pl;
+  if (a.uni_tpr) {
+    const uint32_t r = tile / a.uni_tpr, i = tile - r * a.uni_tpr;
+    pl.off = a.uni_off0 + (uint64_t)r * a.uni_n; pl.n = a.uni_n; pl.word_off = (uint64_t)r * a.uni_wstride;
+    pl.d0 = a.uni_dl + (int)i * a.T; pl.d1 = min(pl.d0 + a.T, a.uni_dr);
+  } else {
+    pl = a.tiles[tile];
+  }
   const int d0 = pl.d0, d1 = pl.d1;
   const int ns = d1 - d0 + 1;                       // symbols d0 .. d1
   const int64_t N = (int64_t)pl.n;
@@ -1061,6 +1073,25 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
       h->launches++;
     }
     ma.samples = d_samples; ma.tiles = (const PskTile*)h->tiles.p; ma.n_tiles = n_tiles;
+    {
+      // uniform batch?  every recording decodable by the main kernel, same length, back to back, same tile range
+      bool uni = n_rec > 0 && n_tiles > 0 && !getenv("FB_PSK_NO_UNIFORM");
+      const RecPlan& p0 = plans[0];
+      const uint64_t wst = n_rec > 1 ? plans[1].word_off - p0.word_off : 0;
+      for (int r = 0; uni && r < n_rec; ++r) {
+        const RecPlan& q = plans[r];
+        uni = q.status == FB_ST_OK && q.n == p0.n && q.off == p0.off + (uint64_t)r * p0.n && q.dl32 == p0.dl32 && q.dr32 == p0.dr32 &&
+              q.dr32 > q.dl32 && q.word_off == (uint64_t)r * wst && tile_first[r] == (uint32_t)r * tile_first[std::min(1, n_rec - 1)] &&
+              p0.word_off == 0;
+      }
+      if (uni && n_rec > 1 && tile_first[1] == 0) uni = false;
+      ma.uni_tpr = 0;
+      if (uni) {
+        ma.uni_tpr = n_rec > 1 ? tile_first[1] : n_tiles;
+        ma.uni_dl = p0.dl32; ma.uni_dr = p0.dr32; ma.uni_off0 = p0.off; ma.uni_n = p0.n; ma.uni_wstride = wst;
+        if ((uint64_t)ma.uni_tpr * (uint64_t)n_rec != n_tiles) ma.uni_tpr = 0;
+      }
+    }
     ma.pf_dist = (uint32_t)(2 * h->sm_count);        // resident CTAs: two per SM
     ma.pf_dist = 0x7fffffffu;                        // measured: the prefetch costs more than it hides (2 CTAs/SM already overlap)
     if (const char* e = getenv("FB_PSK_PF")) { if (atoi(e) > 0) ma.pf_dist = (uint32_t)atoi(e); }   // tuning knob

@@ -113,3 +113,26 @@ def test_shard_invariance_of_batching(engine):
     rev = [r.raw for r in engine.psk_demod_batch(recs[::-1], d)][::-1]
     single = [engine.psk_demod_batch([x], d)[0].raw for x in recs]
     assert whole == rev == single
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.int16])
+def test_uniform_batch_descriptors(dt, engine, monkeypatch):
+    """Equal-length recordings back to back take the arithmetic tile descriptors (no descriptor table read); the same
+    batch through the table (FB_PSK_NO_UNIFORM=1) and one recording at a time must give identical bytes."""
+    import fbdsp
+    rng = np.random.default_rng(31)
+    n = 96000 * 2 + 13
+    recs = []
+    for k in range(5):
+        _, _, x = sig.kat_signal(sig.qpsk_modulate, 300 + k, 4000, 15, baud=9600, carrier=9600.0)
+        x = np.concatenate([x, (rng.standard_normal(n) * 0.01).astype(np.float32)])[:n]
+        recs.append((x * 20000).astype(np.int16) if dt == np.int16 else x)
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    monkeypatch.delenv("FB_PSK_NO_UNIFORM", raising=False)
+    uni = engine.psk_demod_batch(recs, d)
+    monkeypatch.setenv("FB_PSK_NO_UNIFORM", "1")
+    tab = engine.psk_demod_batch(recs, d)
+    for r, (a, b) in enumerate(zip(uni, tab)):
+        one = engine.psk_demod_batch([recs[r]], d)[0]
+        assert a.raw == b.raw == one.raw and a.sync_idx == b.sync_idx == one.sync_idx and a.status == b.status == 0
+        assert len(a.raw) > 4000
