@@ -167,14 +167,18 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   for (int i = threadIdx.x; i < a.nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
   // ---- this CTA's tile ---------------------------------------------------------------------------------------
   const uint32_t tile = blockIdx.x;
-  PskTile pl;
-  if (a.uni_tpr) {
-    const uint32_t r = tile / a.uni_tpr, i = tile - r * a.uni_tpr;
-    pl.off = a.uni_off0 + (uint64_t)r * a.uni_n; pl.n = a.uni_n; pl.word_off = (uint64_t)r * a.uni_wstride;
-    pl.d0 = a.uni_dl + (int)i * a.T; pl.d1 = min(pl.d0 + a.T, a.uni_dr);
-  } else {
-    pl = a.tiles[tile];
-  }
+  auto get_tile = [&](uint32_t t) {
+    PskTile q;
+    if (a.uni_tpr) {
+      const uint32_t r = t / a.uni_tpr, i = t - r * a.uni_tpr;
+      q.off = a.uni_off0 + (uint64_t)r * a.uni_n; q.n = a.uni_n; q.word_off = (uint64_t)r * a.uni_wstride;
+      q.d0 = a.uni_dl + (int)i * a.T; q.d1 = min(q.d0 + a.T, a.uni_dr);
+    } else {
+      q = a.tiles[t];
+    }
+    return q;
+  };
+  const PskTile pl = get_tile(tile);
   const int d0 = pl.d0, d1 = pl.d1;
   const int ns = d1 - d0 + 1;                       // symbols d0 .. d1
   const int64_t N = (int64_t)pl.n;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   // ---- L2 prefetch for the CTA that will run about one tile-time from now (same SM slot, pf_dist tiles ahead): its
   // staging and boundary loads then hit L2 instead of paying the DRAM latency
   if (tile + a.pf_dist < a.n_tiles) {
-    const PskTile nx = a.tiles[tile + a.pf_dist];
+    const PskTile nx = get_tile(tile + a.pf_dist);
     const int64_t p0 = max((int64_t)0, (int64_t)a.n0 + (int64_t)(nx.d0 - a.dh - PADL) * sps - a.wlen);
     const int64_t p1 = min((int64_t)nx.n, (int64_t)a.n0 + (int64_t)(nx.d1 + 2 + a.dl) * sps + a.wlen);
     const char* base = reinterpret_cast<const char*>(a.samples) + (nx.off + (uint64_t)p0) * sizeof(TIn);
