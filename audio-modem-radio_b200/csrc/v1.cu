@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 //     uniform over a tile (sps % VEC == 0), so the register shift is a warp-uniform switch
 //   * 32 symbols of a warp are always BPSYM whole words: redux.sync OR for BPSYM <= 4, a shuffle gather for wider codes
 //     (OFDM8's 14 bits, 8PSK's 3) -- no shared-memory code table and no CTA barrier for any mode
-struct V1Weights { double2 w[80]; };          // [j * NFU + m], unique rows only
+struct V1Weights { double2 w[80]; float2 wf[8]; };   // [j * NFU + m], unique rows only; wf: float copy of the first 8 (sps 2 pre-slicer)
 
 __device__ __noinline__ uint32_t psk8_code_slow(double I, double Q) { return psk8_code(I, Q); }   // rare: keep it out of line
 
@@ -424,16 +424,37 @@ __global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2
 #pragma unroll
           for (int g = 0; g < SPT; ++g) {
             double fr[NFU], fi[NFU];
+            auto correlate = [&]() {                                          // float64 accumulation (App. B)
 #pragma unroll
-            for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
+              for (int m = 0; m < NFU; ++m) { fr[m] = 0.0; fi[m] = 0.0; }
 #pragma unroll
-            for (int j = 0; j < LEN; ++j) {
-              const double xv = (double)x[g * SPS + j + P];
+              for (int j = 0; j < LEN; ++j) {
+                const double xv = (double)x[g * SPS + j + P];
 #pragma unroll
-              for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
-            }
+                for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
+              }
+            };
+            constexpr bool PRE = MODE == V1_PSK8 && LEN == 2 && NFU == 1;     // float32 pre-slicer, float64 on demand
+            if (!PRE) correlate();
             uint32_t c = 0;
-            if (MODE == V1_QPSK) {                                            // B.5: bit 1 = Q < 0, bit 0 = I < 0
+            if (MODE == V1_PSK8 && LEN == 2 && NFU == 1) {
+              // 2 samples per symbol: the float64 correlation + slicer would run once per 2 samples.  Decide in float32
+              // first; the float32 evaluation is within 7e-7 (|x0| + |x1|) of the float64 one, so a decision whose cross
+              // products (and |Q|: the 0 / 2 pi wrap is a real edge) clear 4e-6 (|x0| + |x1|) is the float64 decision.
+              // Everything else (about 1e-5 of the symbols) takes the float64 path below.
+              const float x0 = x[g * SPS + P], x1 = x[g * SPS + 1 + P];
+              const float If = fmaf(x1, wt.wf[1].x, x0 * wt.wf[0].x), Qf = fmaf(x1, wt.wf[1].y, x0 * wt.wf[0].y);
+              const float ai = fabsf(If), aq = fabsf(Qf), gb = 4e-6f * (fabsf(x0) + fabsf(x1));
+              const float cr1 = fmaf(0.92387953f, aq, -0.38268343f * ai), cr3 = fmaf(0.38268343f, aq, -0.92387953f * ai);
+              if (fabsf(cr1) > gb && fabsf(cr3) > gb && aq > gb) {
+                const uint32_t o = 2u - (__float_as_uint(cr1) >> 31) - (__float_as_uint(cr3) >> 31);
+                const bool in = If < 0.f, qn = Qf < 0.f;
+                c = qn ? (in ? 4u + o : (o < 2u ? 7u : 6u)) : (in ? 4u - o : o);
+              } else {
+                correlate();
+                c = psk8_code_folded(fr[0], fi[0]);
+              }
+            } else if (MODE == V1_QPSK) {                                     // B.5: bit 1 = Q < 0, bit 0 = I < 0
               c = push_sign(push_sign(0u, fi[0]), fr[0]);
               if (fr[0] != fr[0] || fi[0] != fi[0]) c = 2u;
             } else if (MODE == V1_BPSK) c = fr[0] > 0.0 ? 0u : 1u;            // B.4: '0' if I > 0 else '1'
@@ -801,6 +822,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
       V1Weights wt{};
       for (int j = 0; j < p.len; ++j)
         for (int m = 0; m < nfu; ++m) wt.w[j * nfu + m] = make_double2(utab[((size_t)m * p.len + j) * 2], utab[((size_t)m * p.len + j) * 2 + 1]);
+      for (int i = 0; i < 8; ++i) wt.wf[i] = make_float2((float)wt.w[i].x, (float)wt.w[i].y);
 #define FB_V1_SYM(ID, ...)                                                                                              \
       case ID: {                                                                                                        \
         auto kern = v1_sym_kernel<__VA_ARGS__>;                                                                         \
