@@ -4,9 +4,10 @@
 //   zp_fwd_kernel / zp_bwd_kernel (zp_iir.cuh)   scipy.signal.filtfilt in float64: odd extension by padlen, lfilter_zi
 //                                     start-up, DF2T forward then backward.  Chunk-parallel with coalesced traffic; all
 //                                     recordings of a group in one launch per pass.
-//   cuFFT D2Z -> analytic_fill -> cuFFT Z2Z inverse   scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and
-//                                     one length-N inverse FFT over the whole recording (circular); the library FFT is
-//                                     used for this one library-shaped op exactly as the reference uses pocketfft.
+//   cuFFT D2Z -> hilbert_spec -> cuFFT Z2D   scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and one length-N
+//                                     inverse FFT over the whole recording (circular); the library FFT is used for this
+//                                     one library-shaped op exactly as the reference uses pocketfft.  Only the imaginary
+//                                     part needs the inverse (the real part is the input), so it is a real transform.
 // Decision (modem.py:315-323): bits[n] = env_mark[n] > env_space[n]; per bit a majority vote over the centre half
 // (window truncated at the record end; spb < 4 -> empty window -> no bits).  fsk_vote_kernel packs the decided bits
 // into the same big-endian word stream the DPSK kernels write; backend.cu does the magic search and byte packing.
@@ -19,22 +20,25 @@
 
 #define FSK_ORD 6            // butter(3, band) -> 6th order, 7 coefficients
 
-// scipy.signal.hilbert's one-sided mask: h[0] = 1, h[1 .. ceil(N/2)-1] = 2, h[N/2] = 1 (N even), 0 above
-__global__ void __launch_bounds__(FB_THREADS) analytic_fill_kernel(const cufftDoubleComplex* X, cufftDoubleComplex* Z, int64_t N) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
-    cufftDoubleComplex v = make_cuDoubleComplex(0.0, 0.0);
-    if (k <= N / 2) {
-      const double h = (k == 0 || (2 * k == N)) ? 1.0 : 2.0;
-      if (k < (N + 1) / 2 || 2 * k == N) { v = X[k]; v.x *= h; v.y *= h; }
-    }
-    Z[k] = v;
+// scipy.signal.hilbert: x_a = ifft(fft(x) h), h = [1, 2, ..., 2, 1 (N even), 0, ...].  Its real part is x itself and its
+// imaginary part is H = irfft(-j X[k]) over 0 < k < N/2 (DC and Nyquist bins dropped): one real-to-complex and one
+// complex-to-real transform instead of a full complex inverse.  In place on the half spectrum.
+__global__ void __launch_bounds__(FB_THREADS) hilbert_spec_kernel(cufftDoubleComplex* X, int64_t N) {
+  const int64_t nh = N / 2 + 1;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nh; k += (int64_t)gridDim.x * blockDim.x) {
+    const cufftDoubleComplex v = X[k];
+    const bool keep = k > 0 && 2 * k < N;
+    X[k] = keep ? make_cuDoubleComplex(v.y, -v.x) : make_cuDoubleComplex(0.0, 0.0);      // -j (a + j b) = b - j a
   }
 }
 
-// first tone: keep |a|^2; second tone: cmp[n] = env_mark > env_space  (common 1/N scale dropped on both sides)
-__global__ void __launch_bounds__(FB_THREADS) env_kernel(const cufftDoubleComplex* Z, int64_t N, double* env2, uint8_t* cmp, int second) {
+// |x_a|^2 N^2 = (N f)^2 + H^2 (cuFFT's inverse is unnormalised).  First tone: keep it; second tone:
+// cmp[n] = env_mark > env_space  (squares compare like the envelopes; the common N^2 scale drops out)
+__global__ void __launch_bounds__(FB_THREADS) env_kernel(const double* f, const double* H, int64_t N, double* env2, uint8_t* cmp, int second) {
+  const double dn = (double)N;
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-    const double e = hypot(Z[n].x, Z[n].y);
+    const double re = dn * f[n], im = H[n];
+    const double e = re * re + im * im;
     if (!second) env2[n] = e;
     else cmp[n] = env2[n] > e ? 1 : 0;
   }
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(FB_THREADS) fsk_vote_kernel(const uint8_t* cmp
 
 // ------------------------------------------------------------------------------------------------ host side
 struct FskPlans {
-  std::map<int64_t, std::pair<cufftHandle, cufftHandle>> plans;   // N -> (D2Z, Z2Z)
+  std::map<int64_t, std::pair<cufftHandle, cufftHandle>> plans;   // N -> (D2Z, Z2D)
 };
 static std::map<fb_handle*, FskPlans> g_fsk_plans;
 
@@ -76,14 +80,15 @@ void fb_fsk_release(fb_handle* h) {
 }
 
 // Hilbert envelope compare + vote for one recording whose two tone-filtered copies f0, f1 (float64) are ready
-static int fsk_one(fb_handle* h, const fb_fsk_design& d, int64_t N, int64_t nbits, uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2z,
+static int fsk_one(fb_handle* h, const fb_fsk_design& d, int64_t N, int64_t nbits, uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2d,
                    double* f0, double* f1, cufftDoubleComplex* X, cufftDoubleComplex* Z, double* env, uint8_t* cmp) {
   for (int tone = 0; tone < 2; ++tone) {
-    if (cufftExecD2Z(p_d2z, tone ? f1 : f0, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
+    double* ft = tone ? f1 : f0;
+    if (cufftExecD2Z(p_d2z, ft, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
     const int g = (int)std::min<int64_t>(148 * 8, (N + FB_THREADS - 1) / FB_THREADS);
-    analytic_fill_kernel<<<g, FB_THREADS, 0, h->stream>>>(X, Z, N);
-    if (cufftExecZ2Z(p_z2z, Z, Z, CUFFT_INVERSE) != CUFFT_SUCCESS) { h->err = "cufftExecZ2Z failed"; return FB_ECUDA; }
-    env_kernel<<<g, FB_THREADS, 0, h->stream>>>(Z, N, env, cmp, tone);
+    hilbert_spec_kernel<<<g, FB_THREADS, 0, h->stream>>>(X, N);
+    if (cufftExecZ2D(p_z2d, X, reinterpret_cast<double*>(Z)) != CUFFT_SUCCESS) { h->err = "cufftExecZ2D failed"; return FB_ECUDA; }
+    env_kernel<<<g, FB_THREADS, 0, h->stream>>>(ft, reinterpret_cast<const double*>(Z), N, env, cmp, tone);
     h->launches += 2;
   }
   if (nbits > 0) {
@@ -217,7 +222,7 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
             fp.plans.clear();
           }
           cufftHandle a, b;
-          if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2Z, 1) != CUFFT_SUCCESS) {
+          if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2D, 1) != CUFFT_SUCCESS) {
             h->err = "cufftPlan1d failed";
             return FB_ECUDA;
           }
