@@ -200,7 +200,8 @@ def scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets, steps=3):
     for name, (p, table) in {"v1_qpsk_9600": g.psk_params(g.V1_QPSK, 9600, 9600.0), "v1_bpsk_9600": g.psk_params(g.V1_BPSK, 9600, 3000.0),
                              "v1_ofdm8_9600": g.ofdm_params(9600, 8), "v1_ofdm4_4800": g.ofdm_params(4800, 4),
                              "v1_psk8_2400": g.psk_params(g.V1_PSK8, 2400, 12000.0),
-                             "v1_psk8_38400": g.psk_params(g.V1_PSK8, 38400, 12000.0)}.items():
+                             "v1_psk8_38400": g.psk_params(g.V1_PSK8, 38400, 12000.0),
+                             "v1_fsk_9600_goertzel_uart": g.fsk_params(9600, 8000.0, 16000.0, 7500, 16500, True)}.items():
         size = (int(eng.lib.fb_v1_out_bound(ctypes.byref(p), n_samp)) + 7) // 4 * 4
         oo = np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(size)
         buf = torch.empty(n_rec * size + 16, dtype=torch.uint8, device=dev)
@@ -219,6 +220,21 @@ def scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets, steps=3):
         timed(name, lambda dd=dd, oo=oo, buf=buf: eng.psk_demod_raw(dd, batch.data_ptr(), offsets, _lib.FB_F32, flags, buf.data_ptr(), oo,
                                                                      ol.data_ptr(), sy.data_ptr(), st.data_ptr()))
         del buf
+    try:      # v2 FSK (modem.py:298-341) with tones whose Butterworth design is valid (SURVEY 8d config 1 variant)
+        from fbdsp import fsk as fskmod
+        dd = fskmod.fsk_design(9600, 12000.0, 24000.0, float(FS))
+        size = (int(eng.lib.fb_fsk_out_bound(ctypes.byref(dd), n_samp)) + 7) // 4 * 4
+        oo = np.arange(n_rec + 1, dtype=np.uint64) * np.uint64(size)
+        buf = torch.empty(n_rec * size + 16, dtype=torch.uint8, device=dev)
+
+        def f2():
+            rc = eng.lib.fb_fsk_demod_batch(eng.handle, ctypes.byref(dd), n_rec, batch.data_ptr(), offsets.ctypes.data_as(u64p), _lib.FB_F32, flags,
+                                            buf.data_ptr(), oo.ctypes.data_as(u64p), ol.data_ptr(), sy.data_ptr(), st.data_ptr())
+            _lib.check(eng.lib, eng.handle, rc, "fb_fsk_demod_batch")
+        timed("v2_fsk_9600_m12000_s24000", f2)
+        del buf
+    except Exception as e:      # noqa: BLE001  (informational leg: never fail the bench line)
+        out["v2_fsk_9600_m12000_s24000"] = {"error": str(e)[:200]}
     return out
 
 
