@@ -13,9 +13,14 @@
 //             in shared memory and stores them cooperatively in natural order
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
+#include <algorithm>
 
 #define ZP_THREADS 64
 #define ZP_EB 16
+#ifndef ZP_MINB
+#define ZP_MINB 8              // resident CTAs per SM the register budget is held to
+#endif
 
 template <int ORD>
 struct ZpFilt {
@@ -53,7 +58,7 @@ __device__ __forceinline__ double zp_step(const ZpFilt<ORD>& t, double (&z)[ORD]
 // Blocks whose 64 x 16 positions all lie strictly inside the record take a check-free path (plain strided pointers);
 // only the first / last CTA of a recording pays for the odd extension and the end-state logic.
 template <typename TIn, int ORD>
-__global__ void __launch_bounds__(ZP_THREADS) zp_fwd_kernel(const void* samples, const ZpRec* recs, ZpFilt<ORD> t, int L, int W16, double* ybase) {
+__global__ void __launch_bounds__(ZP_THREADS, ZP_MINB) zp_fwd_kernel(const void* samples, const ZpRec* recs, ZpFilt<ORD> t, int L, int W16, double* ybase) {
   __shared__ double xs[ZP_THREADS][ZP_EB + 1];
   const ZpRec rc = recs[blockIdx.y];
   const int64_t N = rc.N, Next = N + 2 * t.pad, nch = rc.nch;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_fwd_kernel(const void* samples,
 }
 
 template <typename TOut, int ORD>
-__global__ void __launch_bounds__(ZP_THREADS) zp_bwd_kernel(const double* ybase, const ZpRec* recs, ZpFilt<ORD> t, int L, int W16, TOut* out) {
+__global__ void __launch_bounds__(ZP_THREADS, ZP_MINB) zp_bwd_kernel(const double* ybase, const ZpRec* recs, ZpFilt<ORD> t, int L, int W16, TOut* out) {
   __shared__ double os[ZP_THREADS][ZP_EB + 1];
   const ZpRec rc = recs[blockIdx.y];
   const int64_t N = rc.N, Next = N + 2 * t.pad, nch = rc.nch;
@@ -198,4 +203,8 @@ __global__ void __launch_bounds__(ZP_THREADS) zp_bwd_kernel(const double* ybase,
 }
 
 // chunk length for a filter with warm-up w: >= 1024, >= w, multiple of 16
-static inline int zp_chunk_len(int w) { return std::max(1024, (w + 15) / 16 * 16); }
+static inline int zp_chunk_len(int w) {
+  int lmin = 1024;
+  if (const char* e = getenv("FB_ZP_L")) lmin = std::max(256, atoi(e) / 16 * 16);   // tuning knob
+  return std::max(lmin, (w + 15) / 16 * 16);
+}
