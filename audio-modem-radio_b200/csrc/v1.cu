@@ -338,7 +338,11 @@ __global__ void __launch_bounds__(V1_THREADS + 32) v1_corr_kernel(const V1Args a
 //     uniform over a tile (sps % VEC == 0), so the register shift is a warp-uniform switch
 //   * 32 symbols of a warp are always BPSYM whole words: redux.sync OR for BPSYM <= 4, a shuffle gather for wider codes
 //     (OFDM8's 14 bits, 8PSK's 3) -- no shared-memory code table and no CTA barrier for any mode
-struct V1Weights { double2 w[80]; float2 wf[8]; };   // [j * NFU + m], unique rows only; wf: float copy of the first 8 (sps 2 pre-slicer)
+struct V1Weights {
+  double2 w[80];       // [j * NFU + m], unique rows only
+  float2 wf[64];       // float copy of the first 64 (float32 pre-pass)
+  uint32_t zmask;      // bit 2m / 2m+1: the re / im weights of unique row m are all zero (e.g. Im of the Nyquist bin): value is +0
+};
 
 __device__ __noinline__ uint32_t psk8_code_slow(double I, double Q) { return psk8_code(I, Q); }   // rare: keep it out of line
 
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2
                 for (int m = 0; m < NFU; ++m) { fr[m] = fma(xv, wt.w[j * NFU + m].x, fr[m]); fi[m] = fma(xv, wt.w[j * NFU + m].y, fi[m]); }
               }
             };
-            constexpr bool PRE = MODE == V1_PSK8 && LEN == 2 && NFU == 1;     // float32 pre-slicer, float64 on demand
+            constexpr bool PRE = (MODE == V1_PSK8 && LEN == 2 && NFU == 1) || (MODE == V1_OFDM && NFU * LEN <= 64);   // float32 first, float64 on demand
             if (!PRE) correlate();
             uint32_t c = 0;
             if (MODE == V1_PSK8 && LEN == 2 && NFU == 1) {
@@ -453,6 +457,40 @@ __global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2
               } else {
                 correlate();
                 c = psk8_code_folded(fr[0], fi[0]);
+              }
+            } else if (MODE == V1_OFDM && NFU * LEN <= 64) {
+              // float32 pre-pass (FFMA2: re and im of a bin in one instruction): every bin value further than the float32
+              // evaluation error from zero has the float64 sign.  |error| <= (LEN + 2) 6e-8 sum|x|; guard 4x that.
+              float2 f[NFU];
+              float sa = 0.f;
+#pragma unroll
+              for (int m = 0; m < NFU; ++m) f[m] = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < LEN; ++j) {
+                const float xv = x[g * SPS + j + P];
+                sa += fabsf(xv);
+#pragma unroll
+                for (int m = 0; m < NFU; ++m) f[m] = __ffma2_rn(make_float2(xv, xv), wt.wf[j * NFU + m], f[m]);
+              }
+              const float gb = (float)(LEN + 8) * 2.4e-7f * sa;
+              bool safe = true;
+#pragma unroll
+              for (int m = 0; m < NFU; ++m)
+                safe = safe && (((wt.zmask >> (2 * m)) & 1u) || fabsf(f[m].x) > gb) && (((wt.zmask >> (2 * m + 1)) & 1u) || fabsf(f[m].y) > gb);
+              if (safe) {
+#pragma unroll
+                for (int m = 0; m < NF; ++m) {
+                  if (m < NFU) c = __funnelshift_l(__float_as_uint(f[m].x), __funnelshift_l(__float_as_uint(f[m].y), c, 1), 1);
+                  else { const int u = LEN - m - 2; c = __funnelshift_l(__float_as_uint(f[u].x), __funnelshift_l(~__float_as_uint(f[u].y), c, 1), 1); }
+                }
+              } else {                                                        // float64 (App. B), also silence and NaN
+                correlate();
+#pragma unroll
+                for (int m = 0; m < NF; ++m) {
+                  if (m < NFU) c = push_sign(push_sign(c, fi[m]), fr[m]);
+                  else { const int u = LEN - m - 2; c = push_sign((c << 1) | (fi[u] > 0.0 ? 1u : 0u), fr[u]); }
+                }
+                if (fr[0] != fr[0] || fi[0] != fi[0]) c = 0xaaaaaaaau >> (32 - 2 * NF);
               }
             } else if (MODE == V1_QPSK) {                                     // B.5: bit 1 = Q < 0, bit 0 = I < 0
               c = push_sign(push_sign(0u, fi[0]), fr[0]);
@@ -829,7 +867,12 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
       V1Weights wt{};
       for (int j = 0; j < p.len; ++j)
         for (int m = 0; m < nfu; ++m) wt.w[j * nfu + m] = make_double2(utab[((size_t)m * p.len + j) * 2], utab[((size_t)m * p.len + j) * 2 + 1]);
-      for (int i = 0; i < 8; ++i) wt.wf[i] = make_float2((float)wt.w[i].x, (float)wt.w[i].y);
+      for (int i = 0; i < 64; ++i) wt.wf[i] = make_float2((float)wt.w[i].x, (float)wt.w[i].y);
+      for (int m = 0; m < nfu && m < 16; ++m) {
+        bool zr = true, zi = true;
+        for (int j = 0; j < p.len; ++j) { zr = zr && wt.w[j * nfu + m].x == 0.0; zi = zi && wt.w[j * nfu + m].y == 0.0; }
+        wt.zmask |= (zr ? 1u : 0u) << (2 * m) | (zi ? 2u : 0u) << (2 * m);
+      }
 #define FB_V1_SYM(ID, ...)                                                                                              \
       case ID: {                                                                                                        \
         auto kern = v1_sym_kernel<__VA_ARGS__>;                                                                         \

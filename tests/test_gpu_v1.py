@@ -245,3 +245,30 @@ def test_v1_sym_kernel_specials(engine):
     y[105] = np.nan
     raw, _ = g.demod_batch([y], *g.psk_params(g.V1_QPSK, 9600, 9600.0), engine)[0]
     assert raw == v1.qpsk_demodulate(y, 9600, 9600.0)
+
+
+def test_v1_ofdm_prepass_fallbacks(engine, monkeypatch):
+    """The float32 pre-pass of the OFDM demap must hand every symbol it cannot certify to the float64 path: constant
+    input (all demapped bins exactly zero), tiny bins next to large ones, a NaN sample -- same bytes as the generic
+    float64 kernel (a direct DFT leaves 1e-17 residues where the restatement's FFT has exact zeros, so the restatement is
+    not the yardstick for these inputs)."""
+    from fbdsp import modem_v1 as g
+    rng = np.random.default_rng(12)
+    n = 40000
+    const = np.full(n, 0.25, np.float32)
+    mixed = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    mixed[1000:3000] = 0.5                                          # a run of symbols whose bins are exactly zero
+    mixed[5000:7000] += np.float32(1e-7) * rng.standard_normal(2000).astype(np.float32)
+    tone = np.cos(2 * np.pi * 12000.0 * np.arange(n) / 96000).astype(np.float32)   # energy in one bin only, others ~1e-8
+    nan = mixed.copy()
+    nan[12345] = np.nan
+    for baud, nsub in ((9600, 8), (4800, 4)):
+        p, table = g.ofdm_params(baud, nsub)
+        recs = [const, mixed, tone, nan]
+        monkeypatch.delenv("FB_V1_GENERIC", raising=False)
+        fast = g.demod_batch(recs, p, table, engine)
+        monkeypatch.setenv("FB_V1_GENERIC", "1")
+        slow = g.demod_batch(recs, p, table, engine)
+        for (a, _), (b, _) in zip(fast, slow):
+            assert a == b
+        monkeypatch.delenv("FB_V1_GENERIC", raising=False)
