@@ -21,6 +21,17 @@ struct ModRec {
 
 __device__ __forceinline__ uint32_t mod_bit(const uint8_t* d, uint64_t i) { return (d[i >> 3] >> (7 - (int)(i & 7))) & 1u; }
 
+// Python's `phase %= two_pi` on non-negative floats is C fmod: the exact remainder x - n y, always representable.  With
+// n = floor(x / y) found by a multiply and corrected by at most one, fma(-n, y, x) rounds an exactly representable value,
+// i.e. not at all -- the same result as fmod() at a fraction of its latency on the sequential walk.
+__device__ __forceinline__ double mod_fmod_pos(double x, double y, double inv_y) {
+  double n = floor(x * inv_y);
+  double r = fma(-n, y, x);
+  if (r < 0.0) { n -= 1.0; r = fma(-n, y, x); }
+  else if (r >= y) { n += 1.0; r = fma(-n, y, x); }
+  return r;
+}
+
 __global__ void __launch_bounds__(32) mod_phase_kernel(const fb_mod_params p, const ModRec* recs, int n_rec, const uint8_t* data,
                                                         double* phases) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,33 +39,48 @@ __global__ void __launch_bounds__(32) mod_phase_kernel(const fb_mod_params p, co
   const ModRec rc = recs[r];
   const uint8_t* d = data + rc.data_off;
   double* ph = phases + rc.sym_off;
+  // one payload byte per trip (its load does not depend on the phase chain, so it runs ahead of it)
   if (p.kind == FB_MOD_DBPSK) {
     // preamble [1, 0] * 40, then the payload bits MSB first; 1 -> += pi (modem.py:33-48)
     double cur = 0.0;
-    for (uint64_t k = 0; k < rc.n_sym; ++k) {
-      const uint32_t bit = k < 80 ? (uint32_t)(~k & 1u) : mod_bit(d, k - 80);
-      if (bit) cur += p.inc[1];
-      ph[k] = cur;
+    for (int k = 0; k < 80; ++k) { if (~k & 1) cur += p.inc[1]; ph[k] = cur; }
+    ph += 80;
+    for (uint64_t i = 0; i < rc.n_bytes; ++i) {
+      const uint32_t byte = d[i];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { if ((byte >> (7 - k)) & 1u) cur += p.inc[1]; ph[k] = cur; }
+      ph += 8;
     }
   } else if (p.kind == FB_MOD_DQPSK) {
     // preamble [0,0]*30 + [1,1]*10, then dibits MSB first; phase change by 2*b0 + b1 (modem.py:150-174)
     double cur = 0.0;
-    for (uint64_t k = 0; k < rc.n_sym; ++k) {
-      uint32_t code;
-      if (k < 40) code = k < 30 ? 0u : 3u;
-      else { const uint64_t b = 2 * (k - 40); code = (mod_bit(d, b) << 1) | mod_bit(d, b + 1); }
-      cur += p.inc[code];
-      ph[k] = cur;
+    for (int k = 0; k < 40; ++k) { cur += p.inc[k < 30 ? 0 : 3]; ph[k] = cur; }
+    ph += 40;
+    const double i0 = p.inc[0], i1 = p.inc[1], i2 = p.inc[2], i3 = p.inc[3];
+    for (uint64_t i = 0; i < rc.n_bytes; ++i) {
+      const uint32_t byte = d[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t code = (byte >> (6 - 2 * k)) & 3u;
+        cur += (code & 2u) ? ((code & 1u) ? i3 : i2) : ((code & 1u) ? i1 : i0);
+        ph[k] = cur;
+      }
+      ph += 4;
     }
   } else {
     // CPFSK: preamble AA AA AA AA; the bit is generated with the phase carried in, then
-    // phase += 2 pi f (spb / fs); phase %= 2 pi  (modem.py:283-293; Python's % on non-negative floats == fmod)
-    const double two_pi = 6.283185307179586;
+    // phase += 2 pi f (spb / fs); phase %= 2 pi  (modem.py:283-293)
+    const double two_pi = 6.283185307179586, inv = 1.0 / 6.283185307179586;
+    const double inc0 = p.inc[0], inc1 = p.inc[1];
     double cur = 0.0;
-    for (uint64_t k = 0; k < rc.n_sym; ++k) {
-      const uint32_t bit = k < 32 ? (uint32_t)(~k & 1u) : mod_bit(d, k - 32);
-      ph[k] = cur;
-      cur = fmod(__dadd_rn(cur, p.inc[bit]), two_pi);
+    for (uint64_t i = 0; i < rc.n_bytes + 4; ++i) {
+      const uint32_t byte = i < 4 ? 0xAAu : d[i - 4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        ph[k] = cur;
+        cur = mod_fmod_pos(__dadd_rn(cur, ((byte >> (7 - k)) & 1u) ? inc1 : inc0), two_pi, inv);
+      }
+      ph += 8;
     }
   }
 }
