@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(FB_THREADS) sync_search_kernel(const RecPlan* 
   const uint32_t* w = bits + pl.word_off;
   unsigned long long best = ~0ull;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (*(volatile unsigned long long*)&sync_raw[blockIdx.y] < i * 32) break;   // an earlier match is already known (monotone, benign race)
+    if (sync_raw[blockIdx.y] < i * 32) break;        // an earlier match is already known (monotone, benign race)
     const uint32_t hi = __byte_perm(w[i], 0, 0x0123);
     const uint32_t lo = (i + 1 < nwords) ? __byte_perm(w[i + 1], 0, 0x0123) : 0u;
     const uint64_t win = ((uint64_t)hi << 32) | lo;
@@ -33,10 +33,8 @@ __global__ void __launch_bounds__(FB_THREADS) sync_search_kernel(const RecPlan* 
         if (pos + 16 <= nbits && pos < best) best = pos;
       }
     }
-    // publish at once: this thread's later words lie further out, and every other thread leaves its stride loop at its
-    // next trip (the match used to be published only after the finder's whole loop, so everybody scanned everything)
-    if (best != ~0ull) { atomicMin(&sync_raw[blockIdx.y], best); break; }
   }
+  if (best != ~0ull) atomicMin(&sync_raw[blockIdx.y], best);
 }
 
 __global__ void __launch_bounds__(FB_THREADS) pack_bytes_kernel(const RecPlan* plans, int bps, const uint32_t* bits,
