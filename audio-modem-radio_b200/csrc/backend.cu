@@ -13,18 +13,21 @@ __global__ void __launch_bounds__(FB_THREADS) sync_init_kernel(unsigned long lon
   if (i < n_rec) sync_raw[i] = ~0ull;
 }
 
+// Words [w_lo, w_hi) of every recording.  Two launches: the head (where the preamble puts the magic of any real
+// recording), then the rest -- whose CTAs return at once for recordings the head already settled.
 __global__ void __launch_bounds__(FB_THREADS) sync_search_kernel(const RecPlan* plans, int bps, const uint32_t* bits,
-                                                                  unsigned long long* sync_raw) {
+                                                                  unsigned long long* sync_raw, uint64_t w_lo, uint64_t w_hi) {
   const RecPlan pl = plans[blockIdx.y];
   const uint64_t nbits = (uint64_t)pl.ndsym * bps;
   if (nbits < 16) return;
-  const uint64_t nwords = (nbits + 31) / 32;
+  if (w_lo > 0 && sync_raw[blockIdx.y] != ~0ull) return;          // found in the head: nothing further out can be first
+  const uint64_t nwords = min((nbits + 31) / 32, w_hi);
   const uint32_t* w = bits + pl.word_off;
   unsigned long long best = ~0ull;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t i = w_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x) {
     if (sync_raw[blockIdx.y] < i * 32) break;        // an earlier match is already known (monotone, benign race)
     const uint32_t hi = __byte_perm(w[i], 0, 0x0123);
-    const uint32_t lo = (i + 1 < nwords) ? __byte_perm(w[i + 1], 0, 0x0123) : 0u;
+    const uint32_t lo = (i + 1 < (nbits + 31) / 32) ? __byte_perm(w[i + 1], 0, 0x0123) : 0u;
     const uint64_t win = ((uint64_t)hi << 32) | lo;
 #pragma unroll 8
     for (int o = 0; o < 32; ++o) {
@@ -82,7 +85,13 @@ int fb_bits_backend(fb_handle* h, int n_rec, const RecPlan* d_plans, const std::
   const int gx_pack = (int)std::min<uint64_t>(64, (max_words + FB_THREADS - 1) / FB_THREADS);
   for (int r0 = 0; r0 < n_rec; r0 += 65535) {
     const int nr = std::min(65535, n_rec - r0);
-    sync_search_kernel<<<dim3(gx_search, nr), FB_THREADS, 0, h->stream>>>(d_plans + r0, bps, d_bits, sr + r0);
+    const uint64_t head = 4096;                                   // words: the first 131 072 bits
+    sync_search_kernel<<<dim3((unsigned)std::min<uint64_t>(gx_search, head / FB_THREADS), nr), FB_THREADS, 0, h->stream>>>(d_plans + r0, bps, d_bits,
+                                                                                                                          sr + r0, 0, head);
+    if (max_words > head) {
+      sync_search_kernel<<<dim3(gx_search, nr), FB_THREADS, 0, h->stream>>>(d_plans + r0, bps, d_bits, sr + r0, head, ~0ull);
+      h->launches += 1;
+    }
     pack_bytes_kernel<<<dim3(gx_pack, nr), FB_THREADS, 0, h->stream>>>(d_plans + r0, bps, d_bits, sr + r0, d_out,
                                                                         d_out_len + r0, d_sync + r0, d_status + r0);
     h->launches += 2;

@@ -136,3 +136,24 @@ def test_uniform_batch_descriptors(dt, engine, monkeypatch):
         one = engine.psk_demod_batch([recs[r]], d)[0]
         assert a.raw == b.raw == one.raw and a.sync_idx == b.sync_idx == one.sync_idx and a.status == b.status == 0
         assert len(a.raw) > 4000
+
+
+def test_sync_beyond_the_search_head(engine):
+    """The magic search runs in two launches (the first 131 072 bits, then the rest).  An unmodulated carrier decides
+    '00' for 8.5 s, so the first "FB" lies beyond the head; a second recording syncs at once and a third never does."""
+    import fbdsp
+    from oracle.frames import frame_data
+    rng = np.random.default_rng(77)
+    t = np.arange(int(8.5 * 96000)) / 96000
+    lead = np.sin(2 * np.pi * 9600.0 * t)
+    payload = rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    body = sig.qpsk_modulate(frame_data("late.bin", payload, 0, 1, 3000, 0), 9600, 9600.0).astype(np.float64)
+    late = sig.add_awgn(np.concatenate([lead, body]).astype(np.float32), 25, rng)
+    early = sig.add_awgn(body.astype(np.float32), 25, rng)
+    never = sig.add_awgn(lead.astype(np.float32), 25, rng)
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    res = engine.psk_demod_batch([late, early, never], d)
+    for x, r in zip((late, early, never), res):
+        st = o2.qpsk_stages(x, 9600, 9600.0)
+        assert r.sync_idx == st["sync"] and r.raw == st["raw"]
+    assert res[0].sync_idx > 131072 + 64 and 0 <= res[1].sync_idx < 200 and res[2].sync_idx == -1
