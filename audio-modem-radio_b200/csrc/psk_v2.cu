@@ -553,10 +553,16 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   pm_mark(5);
   // ---- differential decisions: PM_CH per thread, 32-bit big-endian words assembled across 2 (DQPSK) / 4 (DBPSK) lanes --
   {
+    // warp w only needs the first symbol of warp w + 1: a producer / consumer pair on named barrier w + 1 (64 threads:
+    // the arriving warp and the waiting one) instead of a CTA-wide barrier
     if (lane == 0) s_y0[warp] = y[0];
-    __syncthreads();
+    __syncwarp();
+    if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");
     float nx = __shfl_down_sync(0xffffffffu, y[0].x, 1), nyv = __shfl_down_sync(0xffffffffu, y[0].y, 1);
-    if (lane == 31 && warp + 1 < nwarp) { nx = s_y0[warp + 1].x; nyv = s_y0[warp + 1].y; }
+    if (warp + 1 < nwarp) {
+      asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+      if (lane == 31) { nx = s_y0[warp + 1].x; nyv = s_y0[warp + 1].y; }
+    }
     uint32_t part = 0;
     if (a.bps == 2) {                                 // slicer specialised outside the unrolled loop (uniform branch)
 #pragma unroll
