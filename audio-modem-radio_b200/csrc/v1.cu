@@ -374,6 +374,8 @@ template <int MODE, int SPS, int OFF0, int LEN, int NFU, int NF, int SPT>
 __global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2 : 4) v1_sym_kernel(const V1Args a, const __grid_constant__ V1Weights wt) {
   constexpr int BPSYM = MODE == V1_BPSK ? 1 : MODE == V1_QPSK ? 2 : MODE == V1_PSK8 ? 3 : MODE == V1_OFDM ? 2 * NF : 1;
   constexpr int BPT = BPSYM * SPT;                                            // bits per thread and pass
+  // OFDM over an even FFT length whose last unique bin is the Nyquist bin: its imaginary weights are exactly zero
+  constexpr uint32_t ZM = (MODE == V1_OFDM && LEN % 2 == 0 && NFU == LEN / 2) ? (2u << (2 * (NFU - 1))) : 0u;
   constexpr int STRIDE = SPS * SPT;                                           // samples between consecutive threads
   constexpr int SPAN = (SPT - 1) * SPS + LEN;                                 // samples a thread correlates
   constexpr int VEC = (STRIDE % 4 == 0) ? 4 : (STRIDE % 2 == 0) ? 2 : 1;
@@ -475,8 +477,10 @@ __global__ void __launch_bounds__(V1_THREADS + 32, SPS >= 80 ? 1 : SPS >= 40 ? 2
               const float gb = (float)(LEN + 8) * 2.4e-7f * sa;
               bool safe = true;
 #pragma unroll
-              for (int m = 0; m < NFU; ++m)
-                safe = safe && (((wt.zmask >> (2 * m)) & 1u) || fabsf(f[m].x) > gb) && (((wt.zmask >> (2 * m + 1)) & 1u) || fabsf(f[m].y) > gb);
+              for (int m = 0; m < NFU; ++m) {        // ZM: components that are identically +0 (checked on the host)
+                if (!((ZM >> (2 * m)) & 1u)) safe = safe && fabsf(f[m].x) > gb;
+                if (!((ZM >> (2 * m + 1)) & 1u)) safe = safe && fabsf(f[m].y) > gb;
+              }
               if (safe) {
 #pragma unroll
                 for (int m = 0; m < NF; ++m) {
@@ -719,7 +723,11 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
     if (psk && (p.sps == 10 || p.sps == 2 || p.sps == 20 || p.sps == 40 || p.sps == 80))
       sym_id = (p.sps == 10 ? 0 : p.sps == 2 ? 3 : p.sps == 20 ? 6 : p.sps == 40 ? 14 : 17) + p.mode;
     else if (p.mode == V1_OFDM && p.sps == 10 && p.off0 == 2 && p.len == 8 && nfu == 4 && p.nf == 7 && map[4] == 0x102 && map[5] == 0x101 &&
-             map[6] == 0x100) sym_id = 9;
+             map[6] == 0x100) {
+      bool nyq_im_zero = true;                          // the kernel exempts Im of the Nyquist bin from its guard band at compile time
+      for (int j = 0; j < p.len; ++j) nyq_im_zero = nyq_im_zero && utab[((size_t)3 * p.len + j) * 2 + 1] == 0.0;
+      if (nyq_im_zero) sym_id = 9;
+    }
     else if (p.mode == V1_OFDM && p.sps == 20 && p.off0 == 5 && p.len == 15 && nfu == 4 && p.nf == 4) sym_id = 10;
     else if (p.mode == V1_FSK && p.off0 == 0 && p.len == p.sps && nfu == 2 && (p.sps == 10 || p.sps == 5 || p.sps == 20))
       sym_id = p.sps == 10 ? 11 : p.sps == 5 ? 12 : 13;
@@ -873,6 +881,8 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
         for (int j = 0; j < p.len; ++j) { zr = zr && wt.w[j * nfu + m].x == 0.0; zi = zi && wt.w[j * nfu + m].y == 0.0; }
         wt.zmask |= (zr ? 1u : 0u) << (2 * m) | (zi ? 2u : 0u) << (2 * m);
       }
+      // (informational: the kernels exempt the compile-time set ZM from the guard band -- checked where sym_id is chosen;
+      // any other all-zero row only costs speed, its symbols fall back to float64)
 #define FB_V1_SYM(ID, ...)                                                                                              \
       case ID: {                                                                                                        \
         auto kern = v1_sym_kernel<__VA_ARGS__>;                                                                         \
