@@ -733,7 +733,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
       sym_id = p.sps == 10 ? 11 : p.sps == 5 ? 12 : 13;
   }
   if (sym_id >= 0) G = 1;
-  const int spt = (sym_id >= 3 && sym_id <= 5) ? 4 : 1;                      // symbols per thread (must match the launch table)
+  const int spt = (sym_id >= 3 && sym_id <= 5) ? 5 : 1;                      // symbols per thread (must match the launch table)
   size_t tile_target = 20480;
   if (sym_id >= 0) tile_target = std::max<size_t>(tile_target, (size_t)V1_THREADS * p.sps * 4);   // at least one full pass per tile
   int stages = 2;
@@ -896,9 +896,9 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
         FB_V1_SYM(0, V1_BPSK, 10, 0, 10, 1, 1, 1)
         FB_V1_SYM(1, V1_QPSK, 10, 0, 10, 1, 1, 1)
         FB_V1_SYM(2, V1_PSK8, 10, 0, 10, 1, 1, 1)
-        FB_V1_SYM(3, V1_BPSK, 2, 0, 2, 1, 1, 4)
-        FB_V1_SYM(4, V1_QPSK, 2, 0, 2, 1, 1, 4)
-        FB_V1_SYM(5, V1_PSK8, 2, 0, 2, 1, 1, 4)
+        FB_V1_SYM(3, V1_BPSK, 2, 0, 2, 1, 1, 5)
+        FB_V1_SYM(4, V1_QPSK, 2, 0, 2, 1, 1, 5)
+        FB_V1_SYM(5, V1_PSK8, 2, 0, 2, 1, 1, 5)
         FB_V1_SYM(6, V1_BPSK, 20, 0, 20, 1, 1, 1)
         FB_V1_SYM(7, V1_QPSK, 20, 0, 20, 1, 1, 1)
         FB_V1_SYM(8, V1_PSK8, 20, 0, 20, 1, 1, 1)
