@@ -152,7 +152,7 @@ extern "C" int fb_debug_pm_trace(unsigned long long* t, unsigned int* sm) {
 __device__ __forceinline__ void pm_mark(int) {}
 #endif
 
-template <typename TIn, int NT, int SPS, int PP>
+template <typename TIn, int NT, int SPS, int PP, int NSL>
 __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
@@ -162,9 +162,11 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   __shared__ float2 s_tbl[FB_MAX_SLOW * SLOW_TBL];   // scan multipliers (a.slow_tbl): read at LDS latency inside the dependent scan chain
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
   const int sps = SPS ? SPS : a.sps;
+  const int dh = NT ? NT / 2 : a.dh, dl = NT ? NT / 2 - 1 : a.dl;   // the host rejects designs with dh != nt / 2 or dl != nt / 2 - 1
+  const int nslow = NSL ? NSL : a.nslow;           // NSL > 0: number of slow poles known at compile time (pair loops unroll)
   constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
   pm_mark(0);
-  for (int i = threadIdx.x; i < a.nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
+  for (int i = threadIdx.x; i < nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
   // ---- this CTA's tile ---------------------------------------------------------------------------------------
   const uint32_t tile = blockIdx.x;
   auto get_tile = [&](uint32_t t) {
@@ -184,15 +186,15 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   const int64_t N = (int64_t)pl.n;
   float* X = smem;                                  // [sps][P]   X[j][c] = x[n0 + (ca + c) sps + j]
   const int P = PP ? PP : a.P;                      // PP > 0: row pitch known at compile time (immediate store / load offsets)
-  const int ca = d0 - a.dh - PADL;                  // global column (== symbol index) of staged column 0
-  const int cc = a.dh + PADL;                       // staged column of symbol d0
+  const int ca = d0 - dh - PADL;                  // global column (== symbol index) of staged column 0
+  const int cc = dh + PADL;                       // staged column of symbol d0
   const int64_t n_d0 = (int64_t)a.n0 + (int64_t)d0 * sps;              // sample index of symbol d0
   const int64_t n_e1 = (int64_t)a.n0 + (int64_t)(d1 + 1) * sps;        // first sample after the tile's last column
   // ---- stage samples: thread <-> column (sps consecutive samples), conflict-free row stores ------------
   // A warp reads 32*sps consecutive samples; each 128-byte line is fetched from L2 once and re-hit in L1.
   {
     const int64_t n_a = (int64_t)a.n0 + (int64_t)ca * sps;          // sample index of staged element 0
-    const int ncols = min(P, cc + ns + a.dl + 1);
+    const int ncols = min(P, cc + ns + dl + 1);
     bool done = false;
     if constexpr (SPS > 0 && (SPS & 1) == 0) {
       // pair loads need an even element index: start one sample early when the column start is odd (the parity is
@@ -254,8 +256,8 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   // staging and boundary loads then hit L2 instead of paying the DRAM latency
   if (tile + a.pf_dist < a.n_tiles) {
     const PskTile nx = get_tile(tile + a.pf_dist);
-    const int64_t p0 = max((int64_t)0, (int64_t)a.n0 + (int64_t)(nx.d0 - a.dh - PADL) * sps - a.wlen);
-    const int64_t p1 = min((int64_t)nx.n, (int64_t)a.n0 + (int64_t)(nx.d1 + 2 + a.dl) * sps + a.wlen);
+    const int64_t p0 = max((int64_t)0, (int64_t)a.n0 + (int64_t)(nx.d0 - dh - PADL) * sps - a.wlen);
+    const int64_t p1 = min((int64_t)nx.n, (int64_t)a.n0 + (int64_t)(nx.d1 + 2 + dl) * sps + a.wlen);
     const char* base = reinterpret_cast<const char*>(a.samples) + (nx.off + (uint64_t)p0) * sizeof(TIn);
     const int64_t nbytes = (p1 - p0) * (int64_t)sizeof(TIn);
     for (int64_t b = (int64_t)tid * 128; b < nbytes; b += (int64_t)nthr * 128)
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   }
   // ---- exact start state of the forward slow recursion at column 0 (left record edge) ----------
   const bool near_left = (n_d0 - a.wlen) <= (int64_t)a.n0;          // the boundary sum would reach column 0
-  if (near_left && tid < a.nslow) {
+  if (near_left && tid < nslow) {
     // Fst[0] = sum_{n < n0} p^(n0-n) xL[n],  xL = scipy's odd extension (pad_bp samples) then the constant
     // xL[-pad_bp] for ever (that is what the lfilter_zi start-up of filtfilt's forward pass stands for).
     const double pr = a.slow_p[2 * tid], pi = a.slow_p[2 * tid + 1];
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   // ---- tile-boundary states of the slow recursions (all pole pairs): Fst[d0] and Bfull[d1+1] as direct sums over the
   // previous / next `wlen` samples against the power table {p_a^k, p_b^k} (zero beyond wlen).  2 directions x 4 slices
   // of 128 samples per step, one warp per (direction, slice) job.
-  for (int pair = 0; pair < a.nslow; pair += 2) {
+  for (int pair = 0; pair < nslow; pair += 2) {
     const float4* pw = a.slow_pw4 + (size_t)(pair >> 1) * a.wpad;
     for (int job = warp; job < 8; job += nwarp) {
       const bool fwd = job < 4;
@@ -346,8 +348,8 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   // dependency); inside the tile the recursion runs on per-column features z (FFMA2, weights from the parameter
   // bank), a thread-local fold, a decaying warp-shuffle scan (up for the forward states, down for the backward
   // ones) and a serial carry over the <= 8 warps.
-  for (int pair = 0; pair < a.nslow; pair += 2) {
-    const bool two = pair + 1 < a.nslow;
+  for (int pair = 0; pair < nslow; pair += 2) {
+    const bool two = pair + 1 < nslow;
     const int i1 = two ? pair + 1 : pair;
     const float2 lam0 = a.lam[pair], lam1 = a.lam[i1];
     // (2) per-column features of this thread's columns: z[0],z[1] forward (pole 0,1), z[2],z[3] backward
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
         y[i] = map22(ab1, sc[3].x - x0c[i], sc[3].y, y[i]);
       }
     }
-    if (pair + 2 < a.nslow) __syncthreads();          // s_tot / s_car are rewritten by the next pair
+    if (pair + 2 < nslow) __syncthreads();          // s_tot / s_car are rewritten by the next pair
   }
 
   pm_mark(4);
@@ -840,17 +842,18 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
   if (n_tiles > 0) {
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
-#define FB_LAUNCH_MAIN(NTV, SPSV, PPV)                                                                                                \
+#define FB_LAUNCH_MAIN(NTV, SPSV, PPV, NSLV)                                                                                              \
     do {                                                                                                                                \
-      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      psk_main_kernel<TIn, NTV, SPSV, PPV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
+      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
     } while (0)
-    if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048);     // 9600 sym/s at 96 kHz, full-size tiles
-    else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0);
-    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0);
-    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0);
-    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0);
-    else FB_LAUNCH_MAIN(0, 0, 0);
+    if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
+    else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0);
+    else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0);
+    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0, 0);
+    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0, 0);
+    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0, 0);
+    else FB_LAUNCH_MAIN(0, 0, 0, 0);
 #undef FB_LAUNCH_MAIN
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
