@@ -487,7 +487,16 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       }
       float x0c[PM_CH];                               // x[n_c] of the thread's columns (row 0)
 #pragma unroll
-      for (int i = 0; i < PM_CH; ++i) x0c[i] = active ? X[pm_swz(cc + e0 + i)] : 0.f;
+      for (int i = 0; i < PM_CH; ++i) x0c[i] = 0.f;
+      if (active) {
+        if (NT) {                                     // cc + e0 is a multiple of 4: two aligned 16-byte loads
+          const float4 u0 = *reinterpret_cast<const float4*>(X + pm_swz(cc + e0)), u1 = *reinterpret_cast<const float4*>(X + pm_swz(cc + e0 + 4));
+          x0c[0] = u0.x; x0c[1] = u0.y; x0c[2] = u0.z; x0c[3] = u0.w; x0c[4] = u1.x; x0c[5] = u1.y; x0c[6] = u1.z; x0c[7] = u1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < PM_CH; ++i) x0c[i] = X[pm_swz(cc + e0 + i)];
+        }
+      }
 #pragma unroll
       for (int i = PM_CH - 1; i >= 0; --i) {          // backward: Bfull[col] includes the column; Bst = Bfull - x[n_col]
         sc[2] = cfma2(lam0, sc[2], z[2][i]);
