@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       const int cntb = (int)max((int64_t)0, min((int64_t)a.wlen + 1, N - n_e1));
       const int klo = fwd ? 1 : 0, khi = fwd ? cntf : cntb - 1;
       float2 bs0 = make_float2(0.f, 0.f), bs1 = make_float2(0.f, 0.f);
+      const TIn* xb = reinterpret_cast<const TIn*>(a.samples) + pl.off + (fwd ? n_d0 : n_e1);
       // three 512-sample steps per trip with all their loads in flight together (wlen is ~1200-1800 samples)
       for (int k00 = klo + 4 * (slice * 32 + lane); k00 <= khi; k00 += 3 * 512) {
         float xv[3][4];
@@ -307,8 +308,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
           for (int u = 0; u < 4; ++u) {
             const int kk = k00 + 512 * q + u;
             const int k = min(kk, khi);                           // clamped address; the duplicate is zeroed below
-            const int64_t n = fwd ? n_d0 - k : n_e1 + k;
-            xv[q][u] = load_sample<TIn>(a.samples, pl.off + (uint64_t)n);
+            xv[q][u] = load_sample<TIn>(xb, (uint64_t)(int64_t)(fwd ? -k : k));       // 32-bit offset from the tile edge
             w[q][u] = __ldg(&pw[min(kk, a.wpad - 1)]);
           }
 #pragma unroll
