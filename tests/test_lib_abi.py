@@ -59,3 +59,31 @@ def test_no_gpu_fails_loudly():
         modem.fsk_demodulate(np.zeros(1000, np.float32))
     with pytest.raises(TypeError):
         modem.psk8_demodulate(np.zeros(10), baud=9600, carrier=3000.0)
+
+
+def test_host_only_bounds_and_struct_mirrors():
+    """Pure host entry points (no device work): output bounds of the modulators / v1 demodulators, and the ctypes
+    mirrors of fb_mod_params / fb_v1_params against the C compiler's layout."""
+    import subprocess, tempfile
+    from fbdsp import modulate as m, modem_v1 as g
+    lib = _lib.load()
+    p, base, env = m.psk_mod_params(m.FB_MOD_DQPSK, 9600, 9600.0, 96000)
+    assert lib.fb_mod_out_samples(ctypes.byref(p), 100) == (40 + 4 * 100) * 10          # modem.py:150-186
+    p, base, env = m.psk_mod_params(m.FB_MOD_DBPSK, 4800, 9600.0, 96000)
+    assert lib.fb_mod_out_samples(ctypes.byref(p), 100) == (80 + 8 * 100) * 20          # modem.py:33-65
+    p, t, _ = m.fsk_mod_params(1200, 1200.0, 2200.0, 96000)
+    assert lib.fb_mod_out_samples(ctypes.byref(p), 0) == 8 * 4 * 80                     # preamble only (modem.py:281)
+    q, table = g.psk_params(g.V1_PSK8, 38400, 12000.0)
+    assert q.sps == 2 and lib.fb_v1_out_bound(ctypes.byref(q), 2001) == 1000 * 3 // 8   # App. B.6: bits truncated to x8
+    q, table = g.ofdm_params(9600, 8)
+    assert (q.sps, q.off0, q.len, q.nf, q.bits_per_sym) == (10, 2, 8, 7, 14)             # App. B.7: 7 carriers for OFDM8 @ 9600
+    assert table[3, :, 1].tolist() == [0.0] * 8                                          # Im row of the Nyquist bin is exactly zero
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "sz.c")
+        open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "fbdsp.h"\n'
+                             'int main(){printf("%zu %zu %zu %zu\\n", sizeof(fb_mod_params), offsetof(fb_mod_params, wfreq), sizeof(fb_v1_params), offsetof(fb_v1_params, bp_b));return 0;}\n')
+        exe = os.path.join(td, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        out = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    assert out[0] == ctypes.sizeof(m.fb_mod_params) and out[1] == m.fb_mod_params.wfreq.offset
+    assert out[2] == ctypes.sizeof(g.fb_v1_params) and out[3] == g.fb_v1_params.bp_b.offset
