@@ -108,6 +108,7 @@ extern "C" void* fb_stream(fb_handle* h) { return h ? (void*)h->stream : nullptr
 
 extern "C" int fb_sync(fb_handle* h) {
   if (!h) return FB_EINVAL;
+  FB_LOCK(h);
   FB_CUDA(h, cudaSetDevice(h->device));
   FB_CUDA(h, cudaStreamSynchronize(h->stream));
   FB_CUDA(h, cudaStreamSynchronize(h->stream2));
@@ -124,7 +125,9 @@ extern "C" int fb_set_profiling(fb_handle* h, int on) {
 }
 
 extern "C" float fb_kernel_ms(fb_handle* h) {
-  if (!h || !h->k_recorded) return -1.f;
+  if (!h) return -1.f;
+  FB_LOCK(h);
+  if (!h->k_recorded) return -1.f;
   float ms = -1.f;
   if (cudaEventSynchronize(h->ev_k1) != cudaSuccess) return -1.f;
   if (cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1) != cudaSuccess) return -1.f;

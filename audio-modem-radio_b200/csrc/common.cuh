@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,10 @@ struct EdgeJob {
 };
 
 struct fb_handle {
+  // Every work-submitting entry point holds this for the whole call, so two host threads that share a handle (the
+  // reference calls decode_from_buffer from the Qt GUI thread and from a QThread, filebeep_advanced_v2.py:324,1112) are
+  // serialised instead of interleaving launches and workspace growth.  Recursive: fb_psk_demod_batch re-enters itself.
+  std::recursive_mutex mu;
   int device = 0, sm_count = 148;
   cudaStream_t stream = nullptr, stream2 = nullptr, stream_copy = nullptr;   // work, edge kernels (high priority), host->device staging
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -52,6 +57,8 @@ struct fb_handle {
   std::vector<RecPlan> last_plans;
   int last_bps = 0;
 };
+
+#define FB_LOCK(h) std::lock_guard<std::recursive_mutex> fb_lock__((h)->mu)
 
 #define FB_CUDA(h, call)                                                                       \
   do {                                                                                         \

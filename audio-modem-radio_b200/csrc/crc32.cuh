@@ -49,33 +49,42 @@ __device__ __forceinline__ void crc_tables_init(uint32_t* tab) {
   __syncthreads();
 }
 
+// RO = true: the bytes are read-only for the whole kernel (true inputs) -> ld.global.nc; RO = false: the bytes were
+// written earlier in the SAME kernel (rs_decode_kernel's decoded block): the non-coherent path is undefined for those,
+// so they are read through L2 (ld.global.cg) after the writer's __syncthreads().
+template <bool RO> __device__ __forceinline__ uint32_t crc_ld32(const uint32_t* p) { return RO ? __ldg(p) : __ldcg(p); }
+template <bool RO> __device__ __forceinline__ uint4 crc_ld128(const uint4* p) { return RO ? __ldg(p) : __ldcg(p); }
+template <bool RO> __device__ __forceinline__ uint8_t crc_ld8(const uint8_t* p) { return RO ? __ldg(p) : __ldcg(p); }
+
 // remainder of data[0..len) starting from state 0
+template <bool RO = true>
 __device__ __forceinline__ uint32_t crc_raw_segment(const uint32_t* tab, const uint8_t* p, uint64_t len) {
   uint32_t c = 0;
-  while (len && ((uintptr_t)p & 3)) { c = tab[(c ^ *p++) & 0xFF] ^ (c >> 8); --len; }
+  while (len && ((uintptr_t)p & 3)) { c = tab[(c ^ crc_ld8<RO>(p++)) & 0xFF] ^ (c >> 8); --len; }
   const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
 #define CRC_WORD(wv)                                                                                              \
   do {                                                                                                            \
     c ^= (wv);                                                                                                    \
     c = tab[768 + (c & 0xFF)] ^ tab[512 + ((c >> 8) & 0xFF)] ^ tab[256 + ((c >> 16) & 0xFF)] ^ tab[c >> 24];      \
   } while (0)
-  while (len >= 4 && ((uintptr_t)p4 & 15)) { CRC_WORD(__ldg(p4)); ++p4; len -= 4; }
+  while (len >= 4 && ((uintptr_t)p4 & 15)) { CRC_WORD(crc_ld32<RO>(p4)); ++p4; len -= 4; }
   // 32 bytes per trip: both 16-byte loads are issued before the (serial) table walk over their eight words
   for (; len >= 32; len -= 32) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p4)), b = __ldg(reinterpret_cast<const uint4*>(p4) + 1);
+    const uint4 a = crc_ld128<RO>(reinterpret_cast<const uint4*>(p4)), b = crc_ld128<RO>(reinterpret_cast<const uint4*>(p4) + 1);
     CRC_WORD(a.x); CRC_WORD(a.y); CRC_WORD(a.z); CRC_WORD(a.w);
     CRC_WORD(b.x); CRC_WORD(b.y); CRC_WORD(b.z); CRC_WORD(b.w);
     p4 += 8;
   }
-  for (; len >= 4; len -= 4) { CRC_WORD(__ldg(p4)); ++p4; }
+  for (; len >= 4; len -= 4) { CRC_WORD(crc_ld32<RO>(p4)); ++p4; }
 #undef CRC_WORD
   p = reinterpret_cast<const uint8_t*>(p4);
-  while (len--) c = tab[(c ^ *p++) & 0xFF] ^ (c >> 8);
+  while (len--) c = tab[(c ^ crc_ld8<RO>(p++)) & 0xFF] ^ (c >> 8);
   return c;
 }
 
 // zlib.crc32(data[0..len)) computed by the whole CTA; the result is valid in every thread.
 // scratch: 33 uint32 of shared memory.  All threads of the CTA must call it.
+template <bool RO = true>
 __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, uint32_t* scratch, const uint8_t* data, uint64_t len) {
   const int nt = blockDim.x, t = threadIdx.x;
   uint64_t seg = (len + nt - 1) / nt;
@@ -83,7 +92,7 @@ __device__ __forceinline__ uint32_t block_crc32(const uint32_t* tab, uint32_t* s
   const uint64_t lo = min(len, (uint64_t)t * seg), hi = min(len, lo + seg);
   uint32_t c = 0;
   if (hi > lo) {
-    c = crc_raw_segment(tab, data + lo, hi - lo);
+    c = crc_raw_segment<RO>(tab, data + lo, hi - lo);
     if (len - hi) c = gf2_mulmod(c, gf2_xpow8n(len - hi));
   }
   if (t == 0) c ^= gf2_mulmod(0xFFFFFFFFu, gf2_xpow8n(len));   // init state 0xFFFFFFFF carried through len bytes

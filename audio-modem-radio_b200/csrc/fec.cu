@@ -47,9 +47,8 @@ __global__ void __launch_bounds__(FB_THREADS) rs_decode_kernel(const FecBlock* b
     }
   }
   if (threadIdx.x < tail) dst[2 * ntr + threadIdx.x] = src[3 * ntr + threadIdx.x];   // fec.py:60-62
-  __threadfence_block();
-  __syncthreads();
-  const uint32_t crc = block_crc32(tab, scratch, dst, olen);            // fec.py:65
+  __syncthreads();                                                      // dst is complete and visible to the whole CTA
+  const uint32_t crc = block_crc32<false>(tab, scratch, dst, olen);     // fec.py:65; coherent loads: dst was written by this kernel
   if (threadIdx.x == 0) {
     const uint32_t want = (uint32_t)src[m] | ((uint32_t)src[m + 1] << 8) | ((uint32_t)src[m + 2] << 16) | ((uint32_t)src[m + 3] << 24);
     out_len[blockIdx.x] = olen;
@@ -113,6 +112,7 @@ enum { FEC_RS = 0, FEC_VIT = 1, FEC_CRC = 2 };
 static int fec_batch(fb_handle* h, int op, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
                      const uint64_t* out_offsets, uint64_t* out_len, int32_t* aux, int flags) {
   if (!h || n_blk < 0 || !in_offsets || (op != FEC_CRC && !out_offsets)) return FB_EINVAL;
+  FB_LOCK(h);
   FB_CUDA(h, cudaSetDevice(h->device));
   if (n_blk == 0) return FB_OK;
   std::vector<FecBlock> blocks(n_blk);

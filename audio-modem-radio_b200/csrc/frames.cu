@@ -74,24 +74,24 @@ __global__ void __launch_bounds__(FB_THREADS) parse_frames_kernel(const ParseRec
   __syncthreads();
   int nf = 0;
   uint64_t pbytes = 0;
-  for (int ci = 0; ci < nc; ++ci) {                         // uniform control flow: every thread evaluates the header
-    const uint64_t start = cand[ci];
-    if (start + 30 > len) continue;                         // decoder.py:166
+  // the reference's header checks in the reference's order, then the payload CRC32 by the whole CTA (uniform control flow)
+  auto try_candidate = [&](uint64_t start) {
+    if (start + 30 > len) return;                           // decoder.py:166
     const uint32_t name_len = p[start + 4];
-    if (name_len == 0) continue;                            // decoder.py:170
+    if (name_len == 0) return;                              // decoder.py:170
     const uint64_t meta = start + 5 + name_len;
-    if (meta + 24 > len) continue;                          // decoder.py:179
+    if (meta + 24 > len) return;                            // decoder.py:179
     uint32_t f[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
       f[k] = (uint32_t)p[meta + 4 * k] | ((uint32_t)p[meta + 4 * k + 1] << 8) | ((uint32_t)p[meta + 4 * k + 2] << 16) |
              ((uint32_t)p[meta + 4 * k + 3] << 24);
     const uint32_t dlen = f[4], pcrc = f[5];
-    if (dlen > 50000000u || dlen == 0) continue;            // decoder.py:184
+    if (dlen > 50000000u || dlen == 0) return;              // decoder.py:184
     const uint64_t pay = meta + 24;
-    if (pay + dlen > len) continue;                         // decoder.py:187
+    if (pay + dlen > len) return;                           // decoder.py:187
     const uint32_t crc = block_crc32(tab, scratch, p + pay, dlen);
-    if (crc != pcrc) continue;                              // decoder.py:195
+    if (crc != pcrc) return;                                // decoder.py:195
     if (threadIdx.x == 0 && nf < max_frames) {
       fb_frame& o = frames[(size_t)r * max_frames + nf];
       o.offset = start; o.name_off = start + 5; o.payload_off = pay;
@@ -100,9 +100,37 @@ __global__ void __launch_bounds__(FB_THREADS) parse_frames_kernel(const ParseRec
     }
     ++nf;
     pbytes += dlen;
+  };
+  if (n_cand <= MAX_CAND) {
+    for (int ci = 0; ci < nc; ++ci) try_candidate(cand[ci]);
+  } else {
+    // More "FBPC" hits than the table holds (a payload that contains the magic many times, e.g. this project's own
+    // sources): walk the stream in order, MAX_CAND * 4 bytes at a time -- a window of that size cannot hold more than
+    // MAX_CAND non-overlapping 4-byte patterns -- so no candidate is ever dropped (the reference parser has no limit).
+    __shared__ int win_cnt;
+    const uint64_t WIN = (uint64_t)MAX_CAND * 4;
+    for (uint64_t w0 = 0; w0 + 4 <= len; w0 += WIN) {
+      __syncthreads();
+      if (threadIdx.x == 0) win_cnt = 0;
+      __syncthreads();
+      for (uint64_t i = w0 + threadIdx.x; i < w0 + WIN && i + 4 <= len; i += blockDim.x)
+        if (p[i] == 'F' && p[i + 1] == 'B' && p[i + 2] == 'P' && p[i + 3] == 'C') cand[atomicAdd(&win_cnt, 1)] = i;
+      __syncthreads();
+      const int wc = win_cnt;
+      if (threadIdx.x == 0) {
+        for (int a = 1; a < wc; ++a) {
+          const unsigned long long v = cand[a];
+          int b = a - 1;
+          while (b >= 0 && cand[b] > v) { cand[b + 1] = cand[b]; --b; }
+          cand[b + 1] = v;
+        }
+      }
+      __syncthreads();
+      for (int ci = 0; ci < wc; ++ci) try_candidate(cand[ci]);
+    }
   }
   if (threadIdx.x == 0) {
-    n_frames[r] = (n_cand > MAX_CAND) ? -nf - 1 : nf;       // negative: candidate list overflowed (host re-parses)
+    n_frames[r] = nf;                                       // may exceed max_frames: only the first max_frames are stored
     payload_bytes[r] = pbytes;
   }
 }
@@ -111,6 +139,7 @@ extern "C" int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw
                                      const uint64_t* raw_len, int max_frames, fb_frame* frames, int32_t* n_frames,
                                      uint64_t* payload_bytes, int flags) {
   if (!h || n_rec < 0 || !raw_offsets || !raw_len || max_frames < 1 || !frames || !n_frames || !payload_bytes) return FB_EINVAL;
+  FB_LOCK(h);
   FB_CUDA(h, cudaSetDevice(h->device));
   if (n_rec == 0) return FB_OK;
   std::vector<ParseRec> recs(n_rec);

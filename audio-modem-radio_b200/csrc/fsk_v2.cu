@@ -111,6 +111,7 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
                                   int dtype, int flags, uint8_t* out, const uint64_t* out_offsets, uint64_t* out_len,
                                   int64_t* sync_idx, int32_t* status) {
   if (!h || !dp || n_rec < 0 || !offsets || !out_offsets) return FB_EINVAL;
+  FB_LOCK(h);
   if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
   const fb_fsk_design& d = *dp;
   if (d.spb < 1 || d.pad < 1) return FB_EINVAL;

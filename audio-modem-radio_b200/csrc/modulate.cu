@@ -119,6 +119,7 @@ extern "C" uint64_t fb_mod_out_samples(const fb_mod_params* p, uint64_t n_bytes)
 extern "C" int fb_modulate_batch(fb_handle* h, const fb_mod_params* pp, const double* base, const double* env, int n_rec,
                                  const uint8_t* data, const uint64_t* data_offsets, float* out, const uint64_t* out_offsets, int flags) {
   if (!h || !pp || !base || n_rec < 0 || !data_offsets || !out_offsets) return FB_EINVAL;
+  FB_LOCK(h);
   const fb_mod_params& p = *pp;
   if (p.kind < FB_MOD_DBPSK || p.kind > FB_MOD_CPFSK || p.sps < 0 || p.sps > 1 << 20) return FB_EINVAL;
   if (p.kind != FB_MOD_CPFSK && !env) return FB_EINVAL;

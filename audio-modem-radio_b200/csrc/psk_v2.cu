@@ -878,6 +878,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
                                   uint8_t* out, const uint64_t* out_offsets, uint64_t* out_len, int64_t* sync_idx,
                                   int32_t* status) {
   if (!h || !dp || n_rec < 0 || !offsets || !out_offsets) return FB_EINVAL;
+  FB_LOCK(h);
   if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
   const fb_psk_design& d = *dp;
   if (d.sps < 1 || (d.bits_per_sym != 1 && d.bits_per_sym != 2)) return FB_EINVAL;
@@ -1157,7 +1158,9 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
 }
 
 extern "C" int fb_psk_last_bits(fb_handle* h, int rec, uint8_t* bits_out, uint64_t cap_bytes, uint64_t* n_bits) {
-  if (!h || rec < 0 || rec >= (int)h->last_plans.size() || !n_bits) return FB_EINVAL;
+  if (!h || !n_bits) return FB_EINVAL;
+  FB_LOCK(h);
+  if (rec < 0 || rec >= (int)h->last_plans.size()) return FB_EINVAL;
   const RecPlan& p = h->last_plans[rec];
   *n_bits = (uint64_t)p.ndsym * h->last_bps;
   const uint64_t nbytes = (*n_bits + 7) / 8;

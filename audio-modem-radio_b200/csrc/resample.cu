@@ -66,6 +66,7 @@ static int rs_plan(fb_handle* h, int64_t len, int inverse, cufftHandle* out) {
 extern "C" int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frames, int n_channels, int dtype, uint64_t n_out,
                                   double* out, int flags) {
   if (!h || !in || !out || n_channels < 1 || n_frames < 1 || n_out < 1) return FB_EINVAL;
+  FB_LOCK(h);
   if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
   if (n_frames > ((uint64_t)1 << 31) - 64 || n_out > ((uint64_t)1 << 31) - 64) return FB_EUNSUPPORTED;
   FB_CUDA(h, cudaSetDevice(h->device));

@@ -675,6 +675,7 @@ extern "C" int fb_v1_demod_batch(fb_handle* h, const fb_v1_params* pp, const dou
                                  const uint64_t* offsets, int dtype, int flags, uint8_t* out, const uint64_t* out_offsets,
                                  uint64_t* out_len, int32_t* status) {
   if (!h || !pp || !table || n_rec < 0 || !offsets || !out_offsets) return FB_EINVAL;
+  FB_LOCK(h);
   if (dtype != FB_F32 && dtype != FB_F64 && dtype != FB_S16) return FB_EINVAL;
   if ((flags & FB_SAMPLES_ON_DEVICE) && ((uintptr_t)samples & 15)) return FB_EINVAL;   // bulk copies need a 16-byte aligned batch buffer
   const fb_v1_params& p = *pp;

@@ -15,6 +15,7 @@ Host-side integer / bytes logic: no device work here (the payload CRCs were alre
 from __future__ import annotations
 
 import binascii
+import re
 from typing import Dict, Iterable, List, Optional
 
 
@@ -87,21 +88,44 @@ class FileAssembly:
                 "max_quality": max(q) if q else 0, "completed_parts": self.received_parts, "total_parts": self.total_parts}
 
 
-def assemble_stream(frames: Iterable[dict]) -> Dict[str, dict]:
+_PART_RE = re.compile(r"\.part\d+$")
+
+
+def file_key(fr: dict):
+    """(key, file name) of the file a frame belongs to.  The sender names the parts of a split file "<file>.part<i+1>"
+    (encoder.py:149) and stamps every part with the whole file's CRC32, so the file is "<file>_<file_crc>": the
+    reference's own key (decoder.py:251) keeps the suffix, which is why its multi-part branch can never join anything."""
+    name = fr["name"]
+    base = _PART_RE.sub("", name) if int(fr.get("total", 1)) > 1 else name
+    return f"{base}_{fr['final_crc']}", base
+
+
+def part_payload(fr: dict, decompress: bool = True) -> bytes:
+    """The bytes of the ORIGINAL file this frame carries.  The sender compresses every part on its own before framing
+    (encoder.py:165-168, adaptive_compress, on by default) and the one live receive path decompresses per frame
+    (decoder.py:446), so size / CRC32 of the joined file only hold on the decompressed parts."""
+    if not decompress:
+        return fr["data"]
+    from .decoder import _decompress
+    return _decompress(fr["data"])
+
+
+def assemble_stream(frames: Iterable[dict], decompress: bool = True) -> Dict[str, dict]:
     """Feed parsed frames ({'name','data','final_crc','part','total','file_size'}, e.g. fbdsp.frames.parse_batch(...,
     full=True) over every recording of a job, in arrival order) through FileAssembly objects the way save_decoded_files
     does (decoder.py:247-275): a file is emitted -- and its assembly dropped -- the moment its last part arrives; a later
-    copy of a part then starts a fresh assembly.  Returns {key: {...}} for every file emitted or still pending."""
+    copy of a part then starts a fresh assembly.  Parts are decompressed one by one (part_payload) and keyed by
+    file_key(), the same rule fbdsp.shard.assemble_parts uses.  Returns {key: {...}} for every file emitted or pending."""
     live: Dict[str, FileAssembly] = {}
     out: Dict[str, dict] = {}
     emitted = 0
     for fr in frames:
         total = int(fr.get("total", 1))
-        key = f"{fr['name']}_{fr['final_crc']}"
+        key, base = file_key(fr)
         asm = live.get(key)
         if asm is None:
-            asm = live[key] = FileAssembly(fr["name"], total, int(fr.get("file_size", 0)), int(fr["final_crc"]))
-        if asm.add_part(int(fr.get("part", 0)), fr["data"]):
+            asm = live[key] = FileAssembly(base, total, int(fr.get("file_size", 0)), int(fr["final_crc"]))
+        if asm.add_part(int(fr.get("part", 0)), part_payload(fr, decompress)):
             data = asm.assemble_file()
             rec = {"name": asm.filename, "data": data, "complete": True, "missing": [], "replaced": asm.replaced,
                    "quality": asm.get_quality_report(), **asm.check(data)}

@@ -7,6 +7,7 @@ with their own status, so one bad recording never fails a batch.
 from __future__ import annotations
 
 import ctypes
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -158,14 +159,18 @@ class Engine:
 
 
 _default: Optional[Engine] = None
+_default_lock = threading.Lock()
 
 
 def default_engine() -> Engine:
-    """Process-wide engine on FBDSP_DEVICE (default 0), created on first use."""
+    """Process-wide engine on FBDSP_DEVICE (default 0), created once on first use.  It may be shared by threads (the
+    reference calls decode_from_buffer from the Qt GUI thread and from a QThread, filebeep_advanced_v2.py:324,1112): the
+    library serialises the calls of one handle (include/fbdsp.h)."""
     global _default
-    if _default is None:
-        import os
-        _default = Engine(int(os.environ.get("FBDSP_DEVICE", "0")))
+    with _default_lock:
+        if _default is None:
+            import os
+            _default = Engine(int(os.environ.get("FBDSP_DEVICE", "0")))
     return _default
 
 

@@ -24,20 +24,23 @@ def parse_batch(raws: Sequence[bytes], engine: Engine = None, full: bool = False
     flat = np.zeros(int(off[-1]) + 16, dtype=np.uint8)
     for i, b in enumerate(raws):
         flat[int(off[i]): int(off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
-    frames = (_lib.fb_frame * (n * MAX_FRAMES))()
-    nfr = np.zeros(n, dtype=np.int32)
     pbytes = np.zeros(n, dtype=np.uint64)
-    rc = eng.lib.fb_parse_frames_batch(eng.handle, n, flat.ctypes.data, off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
-                                       lens.ctypes.data, MAX_FRAMES, ctypes.addressof(frames), nfr.ctypes.data,
-                                       pbytes.ctypes.data, 0)
-    _lib.check(eng.lib, eng.handle, rc, "fb_parse_frames_batch")
+    max_frames = MAX_FRAMES
+    while True:
+        frames = (_lib.fb_frame * (n * max_frames))()
+        nfr = np.zeros(n, dtype=np.int32)
+        rc = eng.lib.fb_parse_frames_batch(eng.handle, n, flat.ctypes.data, off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                           lens.ctypes.data, max_frames, ctypes.addressof(frames), nfr.ctypes.data,
+                                           pbytes.ctypes.data, 0)
+        _lib.check(eng.lib, eng.handle, rc, "fb_parse_frames_batch")
+        if int(nfr.max()) <= max_frames:
+            break
+        max_frames = int(nfr.max())        # a recording holds more frames than the table: the reference has no limit, so neither do we
     out = []
     for i, b in enumerate(raws):
-        if nfr[i] < 0 or nfr[i] > MAX_FRAMES:
-            raise _lib.FbdspError(f"recording {i}: more FBPC candidates / frames than the device table holds")
         fl = []
         for k in range(int(nfr[i])):
-            f = frames[i * MAX_FRAMES + k]
+            f = frames[i * max_frames + k]
             rec = {"name": b[f.name_off: f.name_off + f.name_len].decode("utf-8", "ignore"),
                    "data": b[f.payload_off: f.payload_off + f.data_len], "final_crc": int(f.file_crc)}
             if full:

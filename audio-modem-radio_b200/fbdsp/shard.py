@@ -65,22 +65,21 @@ def decode_sharded(recordings: Sequence, lengths: Sequence[int], decode_fn: Call
     return out
 
 
-def assemble_parts(frames: Sequence[dict]) -> Dict[str, dict]:
+def assemble_parts(frames: Sequence[dict], decompress: bool = True) -> Dict[str, dict]:
     """Join multi-part files from parsed frames ({'name','data','final_crc','part','total','file_size'}) gathered from
-    all ranks: fbdsp.assembly.FileAssembly (the reference's semantics, decoder.py:20-116: part slots, a later copy of a
-    part replaces the stored one only when its signal quality is strictly higher, size / CRC32 of the joined file checked
-    against the frame header).  Parts are named "<file>.partN" by the sender (encoder.py:149), so the file is keyed by
-    the base name + file CRC.  Returns {key: {'name','data' | None,'complete','size_ok','crc_ok','missing'}}."""
-    from .assembly import FileAssembly
+    all ranks, in any order: fbdsp.assembly.FileAssembly (the reference's semantics, decoder.py:20-116: part slots, a
+    later copy of a part replaces the stored one only when its signal quality is strictly higher, size / CRC32 of the
+    joined file checked against the frame header).  Every part is decompressed on its own first (the sender compresses
+    per part, encoder.py:165-168) and files are keyed by assembly.file_key() -- one rule for this function and
+    assembly.assemble_stream.  Returns {key: {'name','data' | None,'complete','size_ok','crc_ok','missing'}}."""
+    from .assembly import FileAssembly, file_key, part_payload
     files: Dict[str, FileAssembly] = {}
     for fr in frames:
-        name = fr["name"]
-        base = name.rsplit(".part", 1)[0] if ".part" in name else name
-        key = f"{base}_{fr['final_crc']}"                                       # decoder.py:251
+        key, base = file_key(fr)
         asm = files.get(key)
         if asm is None:
             asm = files[key] = FileAssembly(base, int(fr.get("total", 1)), int(fr.get("file_size", 0)), int(fr["final_crc"]))
-        asm.add_part(int(fr.get("part", 0)), fr["data"])
+        asm.add_part(int(fr.get("part", 0)), part_payload(fr, decompress))
     out = {}
     for key, asm in files.items():
         missing = asm.get_missing_parts()

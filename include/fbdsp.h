@@ -8,8 +8,9 @@
  * Conventions: plain pointers and sizes, no torch / C++ types; caller owns every buffer;
  * return 0 on success or a negative FB_E* code (fb_strerror); per-recording results carry
  * their own FB_ST_* status so one bad recording never fails a batch.  One handle owns one
- * CUDA stream and its device workspace; calls on one handle must not overlap, different
- * handles are independent.  There is NO CPU fallback: every entry point that does work
+ * CUDA stream and its device workspace; calls on one handle from several host threads are
+ * serialised by the library (a per-handle lock held for the whole call), different handles
+ * are independent and run concurrently.  There is NO CPU fallback: every entry point that does work
  * fails with FB_ECUDA when no sm_100 device is usable.
  */
 #ifndef FBDSP_H
@@ -167,8 +168,9 @@ typedef struct fb_frame {
 /* raw stream of recording r: raw[raw_offsets[r] ..) with raw_len[r] valid bytes (raw_offsets HOST, n_rec+1 entries;
  * raw_len lives where `raw` lives: device when FB_SAMPLES_ON_DEVICE -- e.g. fb_psk_demod_batch's out / out_len).
  * frames: n_rec * max_frames records, CRC-valid frames of recording r in stream order at frames[r*max_frames ..];
- * n_frames[r] = count (may exceed max_frames: only the first max_frames are stored; negative = more than 64 "FBPC"
- * candidates, re-parse that recording on the host); payload_bytes[r] = sum of their data_len.                       */
+ * n_frames[r] = count of CRC-valid frames, every "FBPC" occurrence considered (no candidate limit, like the reference);
+ * it may exceed max_frames: only the first max_frames are stored -- call again with a larger table;
+ * payload_bytes[r] = sum of their data_len.                                                                        */
 int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw, const uint64_t* raw_offsets,
                           const uint64_t* raw_len, int max_frames, fb_frame* frames, int32_t* n_frames,
                           uint64_t* payload_bytes, int flags);

@@ -59,3 +59,34 @@ def test_assemble_stream_multi_part_job():
     assert a["complete"] and a["data"] == whole and a["size_ok"] and a["crc_ok"] and a["replaced"] == 1
     b = out["b.bin_7"]
     assert not b["complete"] and b["missing"] == [1] and b["data"] is None
+
+
+MULTI = os.path.join(os.path.dirname(__file__), "golden", "multipart.json")
+
+
+@pytest.mark.parametrize("mode", ["QPSK", "BPSK"])
+def test_multipart_transfer_built_by_the_reference_sender(mode):
+    """Parts split, compressed one by one and framed by the unmodified reference sender (tools/make_golden_multipart.py:
+    encoder.split_file_for_transmission -> adaptive_compress -> _frame_data).  Both join functions must give back the
+    original file -- i.e. decompress per part and key on the base name -- whatever the arrival order."""
+    from fbdsp import shard
+    from fbdsp.assembly import assemble_stream, file_key
+    from oracle.frames import parse_fbp_stream
+    g = json.load(open(MULTI))
+    blob = bytes.fromhex(g["file"])
+    frames = [fr for f in g["modes"][mode] for fr in parse_fbp_stream(bytes.fromhex(f["framed"]), full=True)]
+    assert len(frames) == len(g["modes"][mode]) and any(f["compressed"] for f in g["modes"][mode])
+    assert len({file_key(fr)[0] for fr in frames}) == 1                      # ".partN" names, one file
+    for order in (list(range(len(frames))), list(reversed(range(len(frames)))), [3, 0, 1, 1, 2] + list(range(4, len(frames)))):
+        for join in (assemble_stream, shard.assemble_parts):
+            (f,) = join([frames[i] for i in order]).values()
+            assert f["complete"] and f["data"] == blob and f["size_ok"] and f["crc_ok"] and f["name"] == "notes.txt"
+    (f,) = shard.assemble_parts(frames, decompress=False).values()          # the joined compressed blobs are NOT the file
+    assert f["complete"] and not f["crc_ok"]
+
+
+def test_oracle_parser_has_no_table_limits():
+    from oracle.frames import parse_fbp_stream
+    for s in json.load(open(MULTI))["streams"]:
+        got = parse_fbp_stream(bytes.fromhex(s["raw"]))
+        assert [(f["name"], f["data"].hex(), f["final_crc"]) for f in got] == [(f["name"], f["data"], f["final_crc"]) for f in s["frames"]]

@@ -82,3 +82,31 @@ def test_frame_parser_big_stream_vs_oracle(engine):
     got = frames.parse_batch([s, bytes(corrupted), b""], engine, full=True)
     assert got[0] == ofr.parse_fbp_stream(s, full=True)
     assert got[1] == [] and got[2] == []
+
+
+def test_parser_beyond_the_device_tables(engine):
+    """More than 64 'FBPC' occurrences in one stream and more than 8 frames in one recording (reference outputs recorded by
+    tools/make_golden_multipart.py): the reference parser has no limits, the device parser must not have any either."""
+    import json, os
+    from fbdsp.frames import parse_batch
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "multipart.json")))
+    raws = [bytes.fromhex(s["raw"]) for s in g["streams"]]
+    assert g["streams"][1]["n_magic"] > 64 and len(g["streams"][0]["frames"]) > 8
+    got = parse_batch(raws + [b"FBPC" * 3000, raws[1] * 3], engine)
+    for s, fl in zip(g["streams"], got):
+        assert [(f["name"], f["data"].hex(), f["final_crc"]) for f in fl] == [(f["name"], f["data"], f["final_crc"]) for f in s["frames"]]
+    assert got[2] == []
+    from oracle.frames import parse_fbp_stream
+    assert [(f["name"], f["data"]) for f in got[3]] == [(f["name"], f["data"]) for f in parse_fbp_stream(raws[1] * 3)]
+
+
+def test_multipart_reference_sender_on_device(engine):
+    """The reference sender's compressed multi-part frames through the device parser and the join."""
+    import json, os
+    from fbdsp.frames import parse_batch
+    from fbdsp import shard
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "multipart.json")))
+    blob = bytes.fromhex(g["file"])
+    frames = [fr for fl in parse_batch([bytes.fromhex(f["framed"]) for f in g["modes"]["QPSK"]], engine, full=True) for fr in fl]
+    (f,) = shard.assemble_parts(frames).values()
+    assert f["complete"] and f["data"] == blob and f["crc_ok"] and f["size_ok"]
