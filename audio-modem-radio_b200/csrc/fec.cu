@@ -109,6 +109,9 @@ extern "C" uint64_t fb_viterbi_out_bound(uint64_t n) {
 
 enum { FEC_RS = 0, FEC_VIT = 1, FEC_CRC = 2 };
 
+static int fec_run(fb_handle* h, int op, int n_blk, std::vector<FecBlock>& blocks, uint64_t total_in, uint64_t total_out, const uint8_t* in,
+                   uint8_t* out, uint64_t* out_len, int32_t* aux, int flags);
+
 static int fec_batch(fb_handle* h, int op, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
                      const uint64_t* out_offsets, uint64_t* out_len, int32_t* aux, int flags) {
   if (!h || n_blk < 0 || !in_offsets || (op != FEC_CRC && !out_offsets)) return FB_EINVAL;
@@ -122,7 +125,11 @@ static int fec_batch(fb_handle* h, int op, int n_blk, const uint8_t* in, const u
     blocks[i].out_off = out_offsets ? out_offsets[i] : 0;
     blocks[i].out_cap = out_offsets ? out_offsets[i + 1] - out_offsets[i] : 0;
   }
-  const uint64_t total_in = in_offsets[n_blk], total_out = out_offsets ? out_offsets[n_blk] : 0;
+  return fec_run(h, op, n_blk, blocks, in_offsets[n_blk], out_offsets ? out_offsets[n_blk] : 0, in, out, out_len, aux, flags);
+}
+
+static int fec_run(fb_handle* h, int op, int n_blk, std::vector<FecBlock>& blocks, uint64_t total_in, uint64_t total_out, const uint8_t* in,
+                   uint8_t* out, uint64_t* out_len, int32_t* aux, int flags) {
   int rc;
   if ((rc = fb_ensure(h, h->fec_meta, (size_t)n_blk * sizeof(FecBlock)))) return rc;
   FB_CUDA(h, cudaMemcpyAsync(h->fec_meta.p, blocks.data(), (size_t)n_blk * sizeof(FecBlock), cudaMemcpyHostToDevice, h->stream));
@@ -160,6 +167,24 @@ static int fec_batch(fb_handle* h, int op, int n_blk, const uint8_t* in, const u
 extern "C" int fb_rs_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
                                   const uint64_t* out_offsets, uint64_t* out_len, int32_t* crc_ok, int flags) {
   return fec_batch(h, FEC_RS, n_blk, in, in_offsets, out, out_offsets, out_len, crc_ok, flags);
+}
+
+// Blocks given as (start, length) spans inside `in` -- e.g. the payloads of the frames fb_parse_frames_batch found in the raw
+// streams still resident on the device -- instead of CSR offsets: no gather copy between the parser and the decoder.
+extern "C" int fb_rs_decode_spans(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_start, const uint64_t* in_len,
+                                  uint8_t* out, const uint64_t* out_offsets, uint64_t* out_len, int32_t* crc_ok, int flags) {
+  if (!h || n_blk < 0 || !in_start || !in_len || !out_offsets || !(flags & FB_SAMPLES_ON_DEVICE)) return FB_EINVAL;
+  FB_LOCK(h);
+  FB_CUDA(h, cudaSetDevice(h->device));
+  if (n_blk == 0) return FB_OK;
+  std::vector<FecBlock> blocks(n_blk);
+  for (int i = 0; i < n_blk; ++i) {
+    blocks[i].in_off = in_start[i];
+    blocks[i].in_len = in_len[i];
+    blocks[i].out_off = out_offsets[i];
+    blocks[i].out_cap = out_offsets[i + 1] - out_offsets[i];
+  }
+  return fec_run(h, FEC_RS, n_blk, blocks, 0, out_offsets[n_blk], in, out, out_len, crc_ok, flags);
 }
 
 extern "C" int fb_viterbi_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,

@@ -227,12 +227,15 @@ def corpus_groups(modes: Sequence[str], symbol_rates: Sequence, carriers=None, t
     """decoder.py:422-434 applied to every recording of a corpus, then grouped: {(kind, baud, carrier | (mark, space),
     dtype): [recording indices]} in first-appearance order.  carriers / tones are per-recording overrides of what
     decode_from_buffer hard-wires (carrier 3000.0 via the demodulators' defaults; FSK tones 1200.0 / 2200.0, for which the
-    reference's Butterworth design raises) -- None entries keep the reference's values."""
+    reference's Butterworth design raises) -- None entries keep the reference's values; a tones entry may carry a third
+    element, the bit rate, for FSK rates the three mode strings cannot name."""
     groups = {}
     for i, (mode, sr) in enumerate(zip(modes, symbol_rates)):
         kind, baud = mode_params(mode, sr)
         if kind == "fsk":
-            par = tuple(float(v) for v in tones[i]) if tones is not None and tones[i] is not None else (1200.0, 2200.0)
+            par = tuple(float(v) for v in tones[i][:2]) if tones is not None and tones[i] is not None else (1200.0, 2200.0)
+            if tones is not None and tones[i] is not None and len(tones[i]) > 2:
+                baud = tones[i][2]                                     # (mark, space, baud): bit rates the mode strings cannot name
         else:
             par = float(carriers[i]) if carriers is not None and carriers[i] is not None else 3000.0
         dt = np.dtype(dtypes[i]).str if dtypes is not None else ""

@@ -47,6 +47,24 @@ def _as_samples(x) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def flat_view(recordings: Sequence[np.ndarray]) -> np.ndarray:
+    """The recordings back to back as ONE array: without a copy when they already are consecutive slices of one buffer
+    (e.g. the parts of a pinned staging ring), else concatenated."""
+    if len(recordings) == 1:
+        return np.ascontiguousarray(recordings[0])
+    r0 = recordings[0]
+    if all(r.flags.c_contiguous for r in recordings):
+        p = r0.ctypes.data
+        for r in recordings:
+            if r.ctypes.data != p:
+                break
+            p += r.nbytes
+        else:
+            n = sum(len(r) for r in recordings)
+            return np.ndarray((n,), dtype=r0.dtype, buffer=(ctypes.c_char * (n * r0.itemsize)).from_address(r0.ctypes.data))
+    return np.ascontiguousarray(np.concatenate(recordings))
+
+
 _DT = {np.dtype(np.float32): _lib.FB_F32, np.dtype(np.float64): _lib.FB_F64, np.dtype(np.int16): _lib.FB_S16}
 
 
@@ -132,8 +150,7 @@ class Engine:
             raise ValueError(f"unsupported sample dtype {dt}")
         lengths = [len(r) for r in recordings]
         offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-        flat = recordings[0] if len(recordings) == 1 else np.concatenate(recordings)
-        flat = np.ascontiguousarray(flat)
+        flat = flat_view(recordings)
         out_offsets = self.out_bounds(d, lengths)
         out = np.empty(int(out_offsets[-1]) + 4, dtype=np.uint8)
         n = len(recordings)

@@ -11,7 +11,7 @@ import numpy as np
 from scipy import signal
 
 from . import _lib
-from .engine import PADLEN_MSG, DemodResult, Engine, _DT, _as_samples, default_engine
+from .engine import PADLEN_MSG, DemodResult, Engine, _DT, _as_samples, default_engine, flat_view
 
 
 class fb_fsk_design(ctypes.Structure):
@@ -60,7 +60,7 @@ def fsk_demod_batch(recordings: Sequence[np.ndarray], d: fb_fsk_design, engine: 
         raise ValueError("all recordings of one batch must share a supported dtype")
     lengths = [len(r) for r in recordings]
     offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
-    flat = np.ascontiguousarray(recordings[0] if len(recordings) == 1 else np.concatenate(recordings))
+    flat = flat_view(list(recordings))
     if len(flat) == 0:
         flat = np.zeros(1, dtype=dt)
     sizes = np.array([int(eng.lib.fb_fsk_out_bound(ctypes.byref(d), int(n))) for n in lengths], dtype=np.uint64)

@@ -252,6 +252,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-schemes", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[N-1]: 2 = the headline (default); 3 / 4 / 5 run sharded through fbdsp.shard (tools/bench_configs.py)")
+    ap.add_argument("--scale", type=float, default=1.0, help="configs 3-5: fraction of the stated workload size")
+    ap.add_argument("--wave-gsamples", type=float, default=4.0, help="configs 3-5: samples resident per wave and GPU, in units of 1e9")
+    ap.add_argument("--units", type=int, default=0, help="config 5: total recordings (default 1250 * scale per GPU: weak scaling, 10 000 on 8 GPUs)")
+    ap.add_argument("--no-audit", action="store_true", help="configs 4-5: skip the oracle audit of the outputs")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries (NCCL's version banner, torchrun) also write to fd 1, so keep the
     # real stdout aside for the result line and send everything else to stderr
@@ -267,6 +273,11 @@ def main():
               "fs_hz": FS, "recordings_per_gpu": args.recordings, "seconds_per_recording": args.seconds,
               "snr_db": args.snr, "sample_dtype": "float32 resident in HBM for `value`/roofline; PCM16 host buffers (WAV payload) for `e2e`", "l2": "inputs (GBs) larger than L2, no flush needed",
               "sharding": "independent recordings per rank, no collective in the data path"}
+
+    if args.config != 2 and args.impl != "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        return bench_configs.run(args, args.config, rank, world, local, result_out, ClockSampler)
 
     if args.impl == "reference":
         if rank != 0:

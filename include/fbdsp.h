@@ -152,6 +152,11 @@ uint64_t fb_viterbi_out_bound(uint64_t n);     /* ViterbiDecoder.decode output l
  * (the reference only prints a warning when it does not), 0 otherwise, -1 when the out slot is too small.          */
 int fb_rs_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
                        const uint64_t* out_offsets, uint64_t* out_len, int32_t* crc_ok, int flags);
+/* Same decode for blocks given as (start, length) spans of a DEVICE buffer (FB_SAMPLES_ON_DEVICE required; in_start /
+ * in_len / out_offsets are HOST arrays): the payloads of frames found by fb_parse_frames_batch are decoded where the
+ * demodulator left them, without a gather copy. */
+int fb_rs_decode_spans(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_start, const uint64_t* in_len,
+                       uint8_t* out, const uint64_t* out_offsets, uint64_t* out_len, int32_t* crc_ok, int flags);
 /* Replaces ViterbiDecoder.decode (fec.py:126-155). */
 int fb_viterbi_decode_batch(fb_handle* h, int n_blk, const uint8_t* in, const uint64_t* in_offsets, uint8_t* out,
                             const uint64_t* out_offsets, uint64_t* out_len, int flags);
