@@ -1,5 +1,6 @@
 // Handle management and the small C-ABI entry points of libfbdsp.so.
 #include "common.cuh"
+#include "psk_shared.cuh"
 
 int fb_ensure(fb_handle* h, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return FB_OK;
@@ -89,8 +90,9 @@ extern "C" void fb_destroy(fb_handle* h) {
   cudaStreamSynchronize(h->stream2);
   fb_fsk_release(h);
   fb_resample_release(h);
+  fb_psk_mma_release(h);
   DevBuf* bufs[] = {&h->in, &h->out, &h->out_len, &h->sync_idx, &h->status, &h->bits, &h->plans, &h->tile_first, &h->tiles,
-                    &h->jobs, &h->scratch, &h->taps, &h->slow_w, &h->sync_raw, &h->fec_in, &h->fec_out, &h->fec_meta, &h->misc};
+                    &h->jobs, &h->scratch, &h->taps, &h->slow_w, &h->sync_raw, &h->fec_in, &h->fec_out, &h->fec_meta, &h->misc, &h->redo};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   cudaEventDestroy(h->ev_fork);

@@ -16,6 +16,7 @@
 //
 // Algorithmic HBM bytes per recording: N * sizeof(sample) read + raw bytes written (<= 0.6 %).
 #include "common.cuh"
+#include "psk_shared.cuh"
 
 #include <algorithm>
 #include <math.h>
@@ -30,13 +31,6 @@
 #endif
 #define PM_MAXTAB 3712       // float2 entries of the per-launch constant table (taps + slow-pole row weights)
 #define SLOW_TBL 48          // per pole pair: 32 lane powers, 5 warp-scan multipliers, 9 warp powers (float2 each)
-
-// One main-kernel tile, resolved once per call by psk_tiles_kernel so that a CTA starts with ONE coalesced 32-byte load
-// instead of a dependent search (tile_first -> tile_first -> plans).
-struct __align__(16) PskTile {
-  uint64_t off, n, word_off;    // the recording: first sample (elements), samples, first word of its bit stream
-  int32_t d0, d1;               // differential symbols [d0, d1) of this tile; symbols d0 .. d1
-};
 
 __global__ void __launch_bounds__(256) psk_tiles_kernel(const RecPlan* plans, const uint32_t* tile_first, int n_rec, uint32_t n_tiles,
                                                          int T, PskTile* tiles) {
@@ -58,6 +52,7 @@ __global__ void __launch_bounds__(256) psk_tiles_kernel(const RecPlan* plans, co
 struct PskMainArgs {
   const void* samples;
   const PskTile* tiles;         // one descriptor per CTA
+  const uint32_t* redo;         // non-null: evaluate only tiles redo[1 .. redo[0]] (the ones psk_mma.cu could not take), CTAs stride over the list
   uint32_t n_tiles, pf_dist;    // pf_dist: the tile this many CTAs ahead gets its samples prefetched into L2
   // uniform batch (equal-length recordings back to back, e.g. the parts of one file): the descriptor is arithmetic on
   // these parameters -- no dependent global load at the top of the CTA.  uni_tpr == 0: read tiles[tile].
@@ -167,8 +162,10 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   constexpr int PADL = NT ? (4 - (NT / 2) % 4) % 4 : 0;
   pm_mark(0);
   for (int i = threadIdx.x; i < nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
-  // ---- this CTA's tile ---------------------------------------------------------------------------------------
-  const uint32_t tile = blockIdx.x;
+  // ---- this CTA's tile(s): blockIdx.x, or -- in redo mode -- a stride over the redo list ---------------------------------------
+  const uint32_t n_work = a.redo ? __ldg(&a.redo[0]) : a.n_tiles;
+  for (uint32_t work = blockIdx.x; work < n_work; work += a.redo ? gridDim.x : n_work) {
+  const uint32_t tile = a.redo ? __ldg(&a.redo[1 + work]) : work;
   auto get_tile = [&](uint32_t t) {
     PskTile q;
     if (a.uni_tpr) {
@@ -608,6 +605,8 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     }
   }
   pm_mark(6);
+  if (a.redo) __syncthreads();                          // the next tile of the list reuses the shared arrays
+  }
 }
 
 // =====================================================================================================
@@ -840,7 +839,8 @@ static void make_job(const fb_psk_design& d, int rec, int64_t N, int k_lo, int k
 }
 
 template <typename TIn>
-static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int nthreads, size_t smem, const PskEdgeArgs& ea) {
+static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthreads, size_t smem, const PskEdgeArgs& ea,
+                      bool use_mma, const fb_psk_design& d, const float* taps, int dtype) {
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -848,13 +848,25 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
     psk_edge_kernel<TIn><<<(ea.n_jobs + 31) / 32, 32, 0, h->stream2>>>(ea);
     h->launches++;
   }
-  if (n_tiles > 0) {
+  uint32_t grid = n_tiles;
+  if (n_tiles > 0 && use_mma) {
+    // interior tiles on the tensor pipe (psk_mma.cu); the few tiles it hands back (samples outside the fp16 split's range)
+    // are then evaluated by the fp32 kernel below, CTAs striding over the redo list
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
+    int rc = fb_psk_mma_launch(h, d, taps, ma.samples, dtype, ma.tiles, n_tiles, ma.bits, (uint32_t*)h->redo.p);
+    if (rc) return rc;
+    if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
+    ma.redo = (const uint32_t*)h->redo.p;
+    ma.uni_tpr = 0;
+    grid = std::min<uint32_t>(n_tiles, (uint32_t)(2 * h->sm_count));
+  }
+  if (n_tiles > 0) {
+    if (h->profiling && !use_mma) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
 #define FB_LAUNCH_MAIN(NTV, SPSV, PPV, NSLV)                                                                                              \
     do {                                                                                                                                \
       FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV><<<n_tiles, nthreads, smem, h->stream>>>(ma);                                               \
+      psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV><<<grid, nthreads, smem, h->stream>>>(ma);                                                  \
     } while (0)
     if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
     else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0);
@@ -864,7 +876,7 @@ static int launch_psk(fb_handle* h, const PskMainArgs& ma, uint32_t n_tiles, int
     else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0, 0);
     else FB_LAUNCH_MAIN(0, 0, 0, 0);
 #undef FB_LAUNCH_MAIN
-    if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
+    if (h->profiling && !use_mma) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
   }
   FB_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
@@ -946,6 +958,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   const int wlen = d.wcols * d.sps;
   size_t smem = 0;
   bool emulate_only = d.emulate_only != 0;
+  const bool use_mma = !emulate_only && taps && fb_psk_mma_usable(h, d, taps);
   if (!emulate_only) {
     if ((d.nt & 1) || d.dh != d.nt / 2 || d.dl != d.nt / 2 - 1) return FB_EINVAL;
     const bool spec = d.nt == 14 || d.nt == 16 || d.nt == 18;      // compile-time tap count: window in registers
@@ -957,6 +970,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     size_t budget = 100 * 1024;                                    // two CTAs per SM
     int tmax = PM_THREADS * PM_CH - 32;
     if (const char* e = getenv("FB_PSK_T")) { tmax = std::max(32, std::min(tmax, atoi(e) / 32 * 32)); }   // tuning knob
+    if (use_mma) tmax = fb_psk_mma_tile_syms();                    // both interior kernels share one tile table
     if (const char* e = getenv("FB_PSK_SMEM_KB")) { budget = (size_t)std::max(8, atoi(e)) * 1024; }
     for (T = tmax; T >= 32; T -= 32) {
       P = (T + 1 + PM_CH - 1) / PM_CH * PM_CH + win;
@@ -1090,6 +1104,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
     if ((rc = fb_ensure(h, h->tiles, (size_t)std::max<uint32_t>(1, n_tiles) * sizeof(PskTile)))) return rc;
+    if (use_mma && (rc = fb_ensure(h, h->redo, ((size_t)n_tiles + 2) * 4))) return rc;
     if (n_tiles > 0) {
       psk_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>((const RecPlan*)h->plans.p, (const uint32_t*)h->tile_first.p, n_rec,
                                                                       n_tiles, T, (PskTile*)h->tiles.p);
@@ -1137,9 +1152,10 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   ea.samples = d_samples; ea.plans = (const RecPlan*)h->plans.p; ea.jobs = (const EdgeJob*)h->jobs.p;
   ea.scratch = (double*)h->scratch.p; ea.bits = (uint32_t*)h->bits.p; ea.n_jobs = (int)jobs.size(); ea.d = d;
 
-  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, nthreads, smem, ea);
-  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, nthreads, smem, ea);
-  else rc = launch_psk<int16_t>(h, ma, n_tiles, nthreads, smem, ea);
+  const bool mma_now = use_mma && !emulate_only && T == fb_psk_mma_tile_syms();
+  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
+  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
+  else rc = launch_psk<int16_t>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
   if (rc) return rc;
 
   rc = fb_bits_backend(h, n_rec, (const RecPlan*)h->plans.p, plans, bps, (const uint32_t*)h->bits.p, d_out, d_out_len, d_sync, d_status);

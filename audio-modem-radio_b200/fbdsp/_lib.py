@@ -17,7 +17,7 @@ FB_ST_OK, FB_ST_EMPTY, FB_ST_TOO_SHORT, FB_ST_UNSUPPORTED = 0, 1, 2, 3
 # every symbol include/fbdsp.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "fb_abi_version", "fb_device_count", "fb_strerror", "fb_last_error", "fb_create", "fb_destroy", "fb_stream",
-    "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits",
+    "fb_sync", "fb_kernel_launches", "fb_set_profiling", "fb_kernel_ms", "fb_psk_out_bound", "fb_psk_demod_batch", "fb_psk_last_bits", "fb_debug_mma_band",
     "fb_rs_out_bound", "fb_viterbi_out_bound", "fb_rs_decode_batch", "fb_rs_decode_spans", "fb_viterbi_decode_batch", "fb_crc32_batch",
     "fb_parse_frames_batch", "fb_fsk_out_bound", "fb_fsk_demod_batch", "fb_v1_out_bound", "fb_v1_demod_batch",
     "fb_ingest_resample", "fb_mod_out_samples", "fb_modulate_batch",
@@ -72,6 +72,8 @@ def load() -> ctypes.CDLL:
     lib.fb_psk_demod_batch.restype = c.c_int
     lib.fb_psk_demod_batch.argtypes = [vp, c.POINTER(fb_psk_design), vp, vp, c.c_int, vp, u64p, c.c_int, c.c_int,
                                        u8p, u64p, vp, vp, vp]
+    lib.fb_debug_mma_band.restype = c.c_int
+    lib.fb_debug_mma_band.argtypes = [c.POINTER(fb_psk_design), vp, vp]
     lib.fb_psk_last_bits.restype = c.c_int
     lib.fb_psk_last_bits.argtypes = [vp, c.c_int, vp, c.c_uint64, u64p]
     lib.fb_rs_out_bound.restype = c.c_uint64

@@ -94,6 +94,8 @@ class PskDesign:
     slow_w: np.ndarray = field(default=None, repr=False)      # complex64 [nslow][sps+1]  p^j, j=0..sps
     c_struct: fb_psk_design = field(default=None, repr=False)
     diag: dict = field(default_factory=dict, repr=False)
+    taps64: np.ndarray = field(default=None, repr=False)      # complex128 [sps][nt]: the same taps before rounding
+    res: list = field(default_factory=list, repr=False)       # [(p, R+, R+', R-, R-')] complex128 per slow pole pair
 
 
 def _tf_eval(z, zeros, poles, gain):
@@ -226,6 +228,8 @@ def psk_design(baud: float, carrier: float, samp_rate: float, band_k: float, n0_
                 qq = (t - dl) * sps - j
                 taps[j, t] = cq[qq - q[0]]
         d.taps = taps.astype(np.complex64)
+        d.taps64 = taps
+        d.res = list(res)
         d.slow_w = np.zeros((max(1, d.nslow), sps + 1), dtype=np.complex64)
         r_slow = 0.0
         for i, (p, rp, rpc, rm, rmc) in enumerate(res):

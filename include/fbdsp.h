@@ -105,6 +105,12 @@ int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* d, const float* taps, 
                        uint8_t* out, const uint64_t* out_offsets,
                        uint64_t* out_len, int64_t* sync_idx, int32_t* status);
 
+/* Debug / test hook (host only, no device needed): the float64 band matrix [8 window shifts][240][16] of the tensor-core
+ * DPSK kernel (csrc/psk_mma.cu; algebra in audio-modem-radio_b200/fbdsp/mma_tables.py) for design d, so that the C++ table
+ * builder can be checked against the Python statement of the same algebra.  Returns the number of 16-sample k-steps, or
+ * -1 when the design is not served by that kernel (the fp32 kernel takes it). */
+int fb_debug_mma_band(const fb_psk_design* d, const float* taps, double* bfir_out);
+
 /* Debug / test hook: decided bit stream of the last fb_psk_demod_batch call on this handle
  * (MSB-first packed, recording r at byte offset bit_offsets[r], n_bits[r] valid bits).  Host buffers. */
 int fb_psk_last_bits(fb_handle* h, int rec, uint8_t* bits_out, uint64_t cap_bytes, uint64_t* n_bits);
