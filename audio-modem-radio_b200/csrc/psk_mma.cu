@@ -26,7 +26,11 @@ namespace {
 
 // ---- schedule of the headline class: sps 10, 16 taps per polyphase row (dl 7, dh 8), two slow poles --------------------
 struct Sched10 {
-  static constexpr int SPS = 10, G = 8, SEG = SPS * G, PITCH = SEG + 8;   // halves per staged segment: +8 keeps ldmatrix conflict-free
+  static constexpr int SPS = 10, G = 8, SEG = SPS * G;
+  // A staged segment (8 sps samples) is SEG / 8 slots of 32 bytes plus 16 bytes of padding (336 bytes: the 8 rows of an
+  // ldmatrix phase then fall into 8 different 16-byte bank groups).  A slot arrives as 8 raw fp32 samples (TMA) and is
+  // converted in place to [8 x fp16 hi | 8 x fp16 lo].
+  static constexpr int SEGB = SEG * 4 + 16;
   static constexpr int KS = 15;                       // k-steps of 16 samples: 7 + 70 + 160 = 237 <= 240
   static constexpr int HH0A = 0, HH0B = 12, HH1A = 2, HH1B = 14;          // non-zero 16x8 blocks of B per n-tile [first, last]
   static constexpr int LO0A = 2, LO0B = 10, LO1A = 4, LO1B = 12;          // blocks that get the lo products
@@ -45,6 +49,8 @@ constexpr int ADV_ROWS = 236;              // rows a tile advances by: 1888 symb
 constexpr int TILE_SYMS = ADV_ROWS * 8;    // 1888 differential symbols decided per tile
 constexpr int SEGS = ROWS + 2;             // staged segments: the last row's window reaches 2 segments further
 constexpr float SX = 16384.f;              // 2^14
+constexpr int CHUNK = 16;                  // tiles per scheduling unit (the forward slow-pole state is carried inside a chunk)
+constexpr int TR_TILES = 48;               // tiles per CTA the phase trace covers
 
 struct MmaArgs {
   const void* samples;
@@ -55,13 +61,16 @@ struct MmaArgs {
   const float4* slow_pw4;       // {p_a^k, p_b^k}: direct-sum weights of the forward state at a range start
   int wpad, wlen, n0, pad_bp, bps;
   float2 lam[2];                // p^(8 sps) per pole
-  float2 lam_pow[2][6];         // lam^(2^st), st = 0..4, and lam^32
+  float2 lam_pow[2][7];         // lam^(2^st), st = 0..6
   double slow_p[4];
   float state_scale;            // Sx * Sf: accumulator units of the slow-pole states
   float2 rho;
   uint32_t* bits;
   uint32_t* redo_count;         // redo_list[atomicAdd(redo_count)] = tile
   uint32_t* redo_list;
+  uint32_t* chunk_ctr;          // dynamic scheduling: CTAs claim chunks of CHUNK consecutive tiles
+  long long* trace;             // FB_MMA_TRACE: [CTA][TR_TILES][16] clock64 stamps of the phase boundaries (experiments only)
+  int dbg;                      // timing experiments only (FB_MMA_DBG): 1 = loaders skip their work, 2 = MMA warps skip theirs, 4 = no epilogue
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +93,9 @@ __device__ __forceinline__ void hmma(float (&d)[4], const uint32_t (&a)[4], cons
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
+__device__ __forceinline__ void tr_mark(const MmaArgs& a, uint32_t it, int slot, bool who) {
+  if (a.trace && who && it < TR_TILES) a.trace[((size_t)blockIdx.x * TR_TILES + it) * 16 + slot] = clock64();
+}
 __device__ __forceinline__ void bar_mma() { asm volatile("bar.sync 1, %0;" ::"n"(MMA_THREADS) : "memory"); }
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
@@ -94,339 +106,494 @@ __device__ __forceinline__ float2 mapf(float4 m, float2 f, float2 acc) {  // acc
   return make_float2(fmaf(m.x, f.x, fmaf(m.y, f.y, acc.x)), fmaf(m.z, f.x, fmaf(m.w, f.y, acc.y)));
 }
 
-// 8 consecutive samples starting at element e (a multiple of 8: 16-byte aligned for every storage type), as floats * 2^14
-template <typename T> __device__ __forceinline__ void load8(const void* base, uint64_t e, float (&v)[8]);
-template <> __device__ __forceinline__ void load8<float>(const void* base, uint64_t e, float (&v)[8]) {
-  const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + e);
-  const float4 a = __ldg(p), b = __ldg(p + 1);
-  v[0] = a.x * SX; v[1] = a.y * SX; v[2] = a.z * SX; v[3] = a.w * SX; v[4] = b.x * SX; v[5] = b.y * SX; v[6] = b.z * SX; v[7] = b.w * SX;
-}
-template <> __device__ __forceinline__ void load8<int16_t>(const void* base, uint64_t e, float (&v)[8]) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(base) + e));
-  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {                  // value / 32768 * 2^14 = value / 2: exact
-    v[2 * i] = (float)(int16_t)(w[i] & 0xFFFFu) * 0.5f;
-    v[2 * i + 1] = (float)(int16_t)(w[i] >> 16) * 0.5f;
+// One staging unit = 8 consecutive samples starting at element e (a multiple of 8: 16-byte aligned for every storage type).
+// The raw 16-byte loads of several units are issued back to back (memory-level parallelism), the conversion to floats * 2^14
+// happens when the unit is consumed.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const void* base, uint64_t e) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + e);
+    a = __ldg(p); b = __ldg(p + 1);
   }
-}
-template <> __device__ __forceinline__ void load8<double>(const void* base, uint64_t e, float (&v)[8]) {
-  const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(base) + e);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const double2 a = __ldg(p + i);
-    v[2 * i] = (float)a.x * SX; v[2 * i + 1] = (float)a.y * SX;   // the fp32 kernel rounds to float first, too
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const float2 k = make_float2(SX, SX);
+    const float2 p0 = __fmul2_rn(make_float2(a.x, a.y), k), p1 = __fmul2_rn(make_float2(a.z, a.w), k);
+    const float2 p2 = __fmul2_rn(make_float2(b.x, b.y), k), p3 = __fmul2_rn(make_float2(b.z, b.w), k);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y; v[4] = p2.x; v[5] = p2.y; v[6] = p3.x; v[7] = p3.y;
   }
-}
+};
+template <> struct Raw8<int16_t> {
+  uint4 a;
+  __device__ __forceinline__ void load(const void* base, uint64_t e) { a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(base) + e)); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                // value / 32768 * 2^14 = value / 2: exact
+      v[2 * i] = (float)(int16_t)(w[i] & 0xFFFFu) * 0.5f;
+      v[2 * i + 1] = (float)(int16_t)(w[i] >> 16) * 0.5f;
+    }
+  }
+};
+template <> struct Raw8<double> {
+  double2 a[4];
+  __device__ __forceinline__ void load(const void* base, uint64_t e) {
+    const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(base) + e);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __ldg(p + i);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = (float)a[i].x * SX; v[2 * i + 1] = (float)a[i].y * SX; }   // the fp32 kernel rounds to float first, too
+  }
+};
 template <typename T> __device__ __forceinline__ float load1s(const void* base, uint64_t e) { return load_sample<T>(base, e) * SX; }
 
-// hi = v rounded to 11 significant bits (exact in fp16 for |v| < 65520), lo = fp16(v - hi)
+// hi = v truncated to 11 significant bits (exact in fp16 for |v| < 65520), lo = fp16(v - hi)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const float ha = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
-  const float hb = __uint_as_float((__float_as_uint(b) + 0x1000u) & 0xFFFFE000u);
-  const __half2 h = __floats2half2_rn(ha, hb), l = __floats2half2_rn(a - ha, b - hb);
+  const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  const float2 d = __fadd2_rn(make_float2(a, b), make_float2(-ha, -hb));
+  const __half2 h = __floats2half2_rn(ha, hb), l = __floats2half2_rn(d.x, d.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+constexpr int POST_WARPS = 4, POST_THREADS = 32 * POST_WARPS;
+constexpr int ALL_THREADS = LOAD_THREADS + MMA_THREADS + POST_THREADS;          // 512: warps 0-3 load, 4-11 MMA, 12-15 post
+// Handoff buffers MMA warps -> post warps, laid out for the READER (post thread p owns symbols 16p .. 16p+15 = rows 2p, 2p+1):
+//   U[j][p] (stride US): symbol 16p + j;   Z[f][row] (stride ZS): feature f of a row  -- reads are conflict-free, writes 2-way
+constexpr int US = 121, NU = 16 * US, ZS = 264, NZ = 4 * ZS;
+
 template <typename S> struct Smem {
-  static constexpr int ARR = SEGS * S::PITCH * 2;          // bytes of one fp16 array of a stage
-  static constexpr int STAGE = 2 * ARR;                    // hi then lo
-  static constexpr int O_Z = 2 * STAGE;                    // float2 [ROWS][4]: group features, then states (in place)
-  static constexpr int O_U = O_Z + ROWS * 32;              // float2 [MAIN_ROWS * 8 + 8]: symbols of the tile
-  static constexpr int O_MAX = O_U + (MAIN_ROWS * 8 + 8) * 8;   // float [2][LOAD_THREADS]
-  static constexpr int O_MISC = O_MAX + 2 * LOAD_THREADS * 4;   // warp totals, carry, flags, mbarriers
-  static constexpr int TOTAL = O_MISC + 512;
+  static constexpr int STAGE = SEGS * S::SEGB;             // bytes of one sample stage
+  static constexpr int O_Z = 2 * STAGE;                    // float2 [2][ROWS][4]: group features per tile parity
+  static constexpr int O_U = O_Z + 2 * NZ * 8;             // float2 [2][NU]: in-group symbols (accumulator units) per tile parity
+  static constexpr int O_MAX = O_U + 2 * NU * 8;           // float [2][LOAD_THREADS]
+  static constexpr int O_MISC = O_MAX + 2 * LOAD_THREADS * 4;
+  static constexpr int TOTAL = O_MISC + 1792;
 };
 
 struct Misc {
-  float2 tot[MMA_WARPS][4];      // warp totals of the group scan
+  float4 maps[2 * 8 * 2];        // MmaArgs::maps rearranged for packed FMAs: {m.x, m.z, m.y, m.w}
+  float2 lpow[2][32];            // lam^(2n), n = 0..31, per pole: two rows per post thread
+  float2 tot[POST_WARPS][4];     // warp totals of the group scan
   float2 carry[2][2];            // [tile parity][pole]: forward states entering row 0 (written by the previous tile at its row ADV_ROWS)
-  int ok;                        // the tile's samples fit the fp16 split
-  int pad;
-  uint64_t full[2], empty[2];
+  float2 yex[POST_WARPS + 1];    // first symbol of every post warp (differential across warp edges)
+  int ok[2];                     // [tile parity]: the tile's samples fit the fp16 split
+  uint32_t tile_s[2], tile_u[2]; // tile index travelling with the sample stage / with the handoff buffers (~0u: no more work)
+  uint32_t chunk;                // the loaders' current chunk
+  uint64_t raw[2];               // sample stages: TMA bytes landed
+  uint64_t full[2], empty[2];    // sample stages: converted by the loaders -> MMA warps
+  uint64_t ufull[2], uempty[2];  // symbol / feature buffers: MMA warps -> post warps
 };
 
+__device__ __forceinline__ void bar_post() { asm volatile("bar.sync 2, %0;" ::"n"(POST_THREADS) : "memory"); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// acc + f.x * (m.x, m.y) + f.y * (m.z, m.w): one real 2x2 map of a complex state as two packed FMAs
+__device__ __forceinline__ float2 map2(float4 m, float2 f, float2 acc) {
+  return ffma2(make_float2(f.y, f.y), make_float2(m.z, m.w), ffma2(make_float2(f.x, f.x), make_float2(m.x, m.y), acc));
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// 120 registers per thread at launch (61 440 of the SM's 65 536: the float64 edge kernel's 32-thread CTAs still fit beside a
+// resident CTA of this kernel); the roles then re-balance: loaders 48, MMA warps 168, post warps 96.
 template <typename TIn, typename S>
-__global__ void __launch_bounds__(MMA_THREADS + LOAD_THREADS, 1) psk_mma_kernel(const __grid_constant__ MmaArgs a) {
+__global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   using L = Smem<S>;
   Misc* misc = reinterpret_cast<Misc*>(smem + L::O_MISC);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(&misc->full[0], LOAD_THREADS); mbar_init(&misc->full[1], LOAD_THREADS);
-    mbar_init(&misc->empty[0], MMA_WARPS); mbar_init(&misc->empty[1], MMA_WARPS);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&misc->raw[i], 1); mbar_init(&misc->full[i], LOAD_THREADS); mbar_init(&misc->empty[i], MMA_WARPS);
+      mbar_init(&misc->ufull[i], MMA_WARPS); mbar_init(&misc->uempty[i], POST_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 32) { const float4 m = __ldg(&a.maps[threadIdx.x]); misc->maps[threadIdx.x] = make_float4(m.x, m.z, m.y, m.w); }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {         // lam^(2n) by binary powers
+    const int i = ((int)threadIdx.x - 64) >> 5, n = 2 * (threadIdx.x & 31);
+    float2 pw = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int sft = 0; sft < 6; ++sft) if (n & (1 << sft)) pw = cmulf(pw, a.lam_pow[i][sft]);
+    misc->lpow[i][n >> 1] = pw;
+  }
   __syncthreads();
-  // contiguous tile range of this CTA
-  const uint32_t t_lo = (uint32_t)(((uint64_t)a.n_tiles * blockIdx.x) / gridDim.x), t_hi = (uint32_t)(((uint64_t)a.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  // Work distribution: chunks of CHUNK consecutive tiles claimed from a global counter by the loaders; the tile index then
+  // travels down the pipeline with the data (tile_s with the sample stage, tile_u with the handoff buffers).  A CTA that
+  // starts late (e.g. its SM hosted a CTA of the float64 edge kernel) simply claims fewer chunks.
 
-  if (warp >= MMA_WARPS) {
+  if (wid < LOAD_WARPS) {
+    setmaxnreg_dec<48>();
     // ================================================== loader warps ==================================================
-    const int lt = tid - MMA_THREADS;
-    for (uint32_t t = t_lo, it = 0; t < t_hi; ++t, ++it) {
+    // One elected thread brings the tile's samples in with bulk asynchronous copies (one per 80-sample segment, 320 bytes:
+    // no registers, no load instructions, the whole tile in flight at once); all loader threads then convert the slots in
+    // place.  120 of the 128 threads: thread lt = 10 rg + c owns slot c of segments rg, rg + 12, rg + 24, ... (immediates).
+    const int lt = (int)threadIdx.x;
+    constexpr int UPS = S::SEG / 8, LROWS = 12, NIT = (SEGS + LROWS - 1) / LROWS;
+    const bool lactive = lt < UPS * LROWS;
+    const int rg = lt / UPS, c = lt - rg * UPS;
+    uint32_t t = 0, t_end = 0;
+    for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
-      mbar_wait(&misc->empty[st], ((it >> 1) & 1) ^ 1);
+      tr_mark(a, it, 10, lt == 0);
+      if (t == t_end) {                                  // claim the next chunk (one atomic per CHUNK tiles)
+        asm volatile("bar.sync 3, %0;" ::"n"(LOAD_THREADS) : "memory");      // everybody has read the previous value
+        if (lt == 0) misc->chunk = atomicAdd(a.chunk_ctr, 1u);
+        asm volatile("bar.sync 3, %0;" ::"n"(LOAD_THREADS) : "memory");
+        const uint32_t ch = misc->chunk;
+        t = ch * CHUNK;
+        t_end = min(a.n_tiles, t + CHUNK);
+        if (ch >= (a.n_tiles + CHUNK - 1) / CHUNK) {     // no more work: pass the end marker down the pipeline
+          mbar_wait(&misc->empty[st], ((it >> 1) & 1) ^ 1);
+          if (lt == 0) misc->tile_s[st] = ~0u;
+          mbar_arrive(&misc->full[st]);
+          break;
+        }
+      }
       const PskTile pl = a.tiles[t];
       const int64_t N = (int64_t)pl.n;
       // window origin of row 0, moved down to a multiple of 8 elements of the sample buffer
       const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;     // H+ = 8 sps
       const int sh = (int)((pl.off + (uint64_t)w0) & 7);
       const int64_t w0a = w0 - sh;
-      unsigned char* sb = smem + st * L::STAGE;
+      unsigned char* stage = smem + st * L::STAGE;
+      unsigned char* sb = stage + rg * S::SEGB + c * 32;
+      const bool inb = sizeof(TIn) == 4 && w0a >= 0 && w0a + (int64_t)SEGS * S::SEG <= N;   // raw fp32 tiles go through the TMA path
       float mx = 0.f;
-      for (int u = lt; u < SEGS * (S::SEG / 8); u += LOAD_THREADS) {
-        const int seg = u / (S::SEG / 8), within = (u - seg * (S::SEG / 8)) * 8;
-        const int64_t n = w0a + (int64_t)u * 8;
-        float v[8];
-        if (n >= 0 && n + 8 <= N) {
-          load8<TIn>(a.samples, pl.off + (uint64_t)n, v);
-        } else {
+      mbar_wait(&misc->empty[st], ((it >> 1) & 1) ^ 1);
+      tr_mark(a, it, 11, lt == 0);
+      if (a.dbg & 1) {
+        mx = 1.f;
+      } else if (inb) {
+        // every thread copies exactly the slots it will convert: 16-byte asynchronous copies (no registers, all in flight at
+        // once), then only its own copies have to have landed
+        if (lactive) {
+          const char* src = reinterpret_cast<const char*>(a.samples) + (pl.off + (uint64_t)w0a + (uint64_t)lt * 8) * 4;
+          const uint32_t dst = smem_u32(sb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (n + i >= 0 && n + i < N) ? load1s<TIn>(a.samples, pl.off + (uint64_t)(n + i)) : 0.f;
+          for (int item = 0; item < NIT; ++item) {
+            if (item == NIT - 1 && rg + LROWS * item >= SEGS) break;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + item * (LROWS * S::SEGB)), "l"(src + (size_t)item * (LROWS * S::SEG * 4)) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + item * (LROWS * S::SEGB) + 16), "l"(src + (size_t)item * (LROWS * S::SEG * 4) + 16) : "memory");
+          }
         }
-        uint4 hi, lo;
-        split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (lactive) {
+#pragma unroll 2
+          for (int item = 0; item < NIT; ++item) {
+            if (item == NIT - 1 && rg + LROWS * item >= SEGS) break;
+            unsigned char* q8 = sb + item * (LROWS * S::SEGB);
+            const float4 r0 = *reinterpret_cast<const float4*>(q8), r1 = *reinterpret_cast<const float4*>(q8 + 16);
+            const float2 k = make_float2(SX, SX);
+            const float2 p0 = __fmul2_rn(make_float2(r0.x, r0.y), k), p1 = __fmul2_rn(make_float2(r0.z, r0.w), k);
+            const float2 p2 = __fmul2_rn(make_float2(r1.x, r1.y), k), p3 = __fmul2_rn(make_float2(r1.z, r1.w), k);
+            uint4 hi, lo;
+            split2(p0.x, p0.y, hi.x, lo.x); split2(p1.x, p1.y, hi.y, lo.y); split2(p2.x, p2.y, hi.z, lo.z); split2(p3.x, p3.y, hi.w, lo.w);
+            mx = fmaxf(fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fmaxf(fabsf(p1.x), fabsf(p1.y))), fmaxf(mx, fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fmaxf(fabsf(p3.x), fabsf(p3.y)))));
+            *reinterpret_cast<uint4*>(q8) = hi;
+            *reinterpret_cast<uint4*>(q8 + 16) = lo;
+          }
+        }
+      } else if (lactive) {
+        for (int item = 0; item < NIT; ++item) {                  // tiles at the ends of a recording, and other sample types: guarded loads
+          if (rg + LROWS * item >= SEGS) break;
+          const int64_t n = w0a + (int64_t)lt * 8 + (int64_t)item * (LROWS * S::SEG);
+          float v[8];
+          if (n >= 0 && n + 8 <= N) {
+            Raw8<TIn> r;
+            r.load(a.samples, pl.off + (uint64_t)n);
+            r.get(v);
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(v[i]));
-        const int o = (seg * S::PITCH + within) * 2;
-        *reinterpret_cast<uint4*>(sb + o) = hi;
-        *reinterpret_cast<uint4*>(sb + L::ARR + o) = lo;
+            for (int j = 0; j < 8; ++j) v[j] = (n + j >= 0 && n + j < N) ? load1s<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
+          }
+          uint4 hi, lo;
+          split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(v[j]));
+          *reinterpret_cast<uint4*>(sb + item * (LROWS * S::SEGB)) = hi;
+          *reinterpret_cast<uint4*>(sb + item * (LROWS * S::SEGB) + 16) = lo;
+        }
       }
       reinterpret_cast<float*>(smem + L::O_MAX)[st * LOAD_THREADS + lt] = mx;
+      if (lt == 0) misc->tile_s[st] = t;
+      tr_mark(a, it, 12, lt == 0);
       mbar_arrive(&misc->full[st]);
+      ++t;
     }
     return;
   }
 
-  // ==================================================== MMA warps =====================================================
-  uint2 bf[S::NFRAG];                       // B fragments (taps hi / lo, feature weights hi / lo) of the current shift
-  int cur_sh = -1;
-  float2* Zs = reinterpret_cast<float2*>(smem + L::O_Z);
-  float2* Us = reinterpret_cast<float2*>(smem + L::O_U);
-  const int g = lane >> 2, q = lane & 3;
-  uint64_t prev_off = ~0ull;
-  int prev_d0 = 0;
-
-  for (uint32_t t = t_lo, it = 0; t < t_hi; ++t, ++it) {
-    const int st = it & 1;
-    const PskTile pl = a.tiles[t];
-    const int64_t N = (int64_t)pl.n;
-    const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;
-    const int sh = (int)((pl.off + (uint64_t)w0) & 7);
-    if (sh != cur_sh) {
-      const uint2* src = a.frags + ((size_t)sh * S::NFRAG) * 32 + lane;
-#pragma unroll
-      for (int i = 0; i < S::NFRAG; ++i) bf[i] = __ldg(src + i * 32);
-      cur_sh = sh;
-    }
-    const bool chained = (pl.off == prev_off) && (pl.d0 == prev_d0 + TILE_SYMS);   // forward state carried from the previous tile
-    prev_off = pl.off; prev_d0 = pl.d0;
-
-    // ---- forward slow-pole state at the tile's first group when it cannot be carried: direct sum over the previous wlen
-    // samples (exact start-up state of scipy's filtfilt when the record start is within reach; psk_v2.cu has the algebra)
-    if (!chained && warp == 0) {
-      const int64_t n_d0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS;
-      const bool near_left = (n_d0 - a.wlen) <= (int64_t)a.n0;
-      const int cnt = (int)min((int64_t)a.wlen, n_d0 - (near_left ? (int64_t)a.n0 : (int64_t)0));
-      float2 s0 = make_float2(0.f, 0.f), s1 = s0;
-      for (int k = 1 + lane; k <= cnt; k += 32) {
-        const float x = load_sample<TIn>(a.samples, pl.off + (uint64_t)(n_d0 - k));
-        const float4 w = __ldg(&a.slow_pw4[k]);
-        s0.x = fmaf(x, w.x, s0.x); s0.y = fmaf(x, w.y, s0.y); s1.x = fmaf(x, w.z, s1.x); s1.y = fmaf(x, w.w, s1.y);
+  if (wid < LOAD_WARPS + MMA_WARPS) {
+    setmaxnreg_inc<168>();
+    // ==================================================== MMA warps =====================================================
+    const int tid = (int)threadIdx.x - LOAD_THREADS, warp = tid >> 5;
+    uint2 bf[S::NFRAG];                       // B fragments (taps hi / lo, feature weights hi / lo) of the current shift
+    int cur_sh = -1;
+    const int g = lane >> 2, q = lane & 3;
+    for (uint32_t it = 0;; ++it) {
+      const int st = it & 1;
+      tr_mark(a, it, 0, tid == 0);
+      if (a.trace && tid == 0 && it < TR_TILES) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.trace[((size_t)blockIdx.x * TR_TILES + it) * 16 + 13] = gt; }
+      mbar_wait(&misc->full[st], (it >> 1) & 1);
+      tr_mark(a, it, 1, tid == 0);
+      const uint32_t t = misc->tile_s[st];
+      if (t == ~0u) {                                    // end marker: forward it to the post warps
+        mbar_wait(&misc->uempty[st], ((it >> 1) & 1) ^ 1);
+        if (tid == 0) misc->tile_u[st] = ~0u;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&misc->ufull[st]);
+        break;
       }
+      const PskTile pl = a.tiles[t];
+      const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;
+      const int sh = (int)((pl.off + (uint64_t)w0) & 7);
+      if (sh != cur_sh) {
+        const uint2* src = a.frags + ((size_t)sh * S::NFRAG) * 32 + lane;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, off); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, off);
-        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+        for (int i = 0; i < S::NFRAG; ++i) bf[i] = __ldg(src + i * 32);
+        cur_sh = sh;
       }
-      if (near_left && lane < 2) {
-        // F[0] = sum_{n < n0} p^(n0-n) xL[n], xL = scipy's odd extension (pad_bp samples), then the constant xL[-pad_bp] for ever
-        const double pr = a.slow_p[2 * lane], pi = a.slow_p[2 * lane + 1];
-        const double x0 = load_sample_d<TIn>(a.samples, pl.off);
-        const double cr = 2.0 * x0 - load_sample_d<TIn>(a.samples, pl.off + a.pad_bp);
-        const double den = (1.0 - pr) * (1.0 - pr) + pi * pi;
-        double sr = cr * (1.0 - pr) / den, si = cr * pi / den;
-        for (int n = -a.pad_bp; n < a.n0; ++n) {
-          const double xv = (n < 0) ? 2.0 * x0 - load_sample_d<TIn>(a.samples, pl.off + (uint64_t)(-n)) : load_sample_d<TIn>(a.samples, pl.off + (uint64_t)n);
-          const double tr = pr * sr - pi * si + xv, ti = pr * si + pi * sr;
-          sr = tr; si = ti;
-        }
-        const double fr = pr * sr - pi * si, fi = pr * si + pi * sr;        // Fst[0] = p * s
-        const float4 pw4 = __ldg(&a.slow_pw4[(int)(n_d0 - a.n0)]);
-        const float2 pw = lane == 0 ? make_float2(pw4.x, pw4.y) : make_float2(pw4.z, pw4.w);
-        const float2 add = cmulf(pw, make_float2((float)fr, (float)fi));
-        if (lane == 0) { s0.x += add.x; s0.y += add.y; } else { s1.x += add.x; s1.y += add.y; }
+      if (a.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(&misc->empty[st]); continue; }
+      int okv = 1;
+      if (warp == 0) {                                  // range check of the tile's samples (scaled by 2^14)
+        const float* mxs = reinterpret_cast<const float*>(smem + L::O_MAX) + st * LOAD_THREADS;
+        float m = fmaxf(fmaxf(mxs[lane], mxs[lane + 32]), fmaxf(mxs[lane + 64], mxs[lane + 96]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        okv = (m < 65000.f && m >= 0.0625f) ? 1 : 0;
       }
-      const float2 mine = lane == 0 ? s0 : s1;
-      if (lane < 2) misc->carry[it & 1][lane] = make_float2(mine.x * a.state_scale, mine.y * a.state_scale);
-    }
+      // the symbol / feature buffers of this parity must have been drained by the post warps (two tiles ago)
+      mbar_wait(&misc->uempty[st], ((it >> 1) & 1) ^ 1);
+      if (warp == 0 && lane == 0) { misc->ok[st] = okv; misc->tile_u[st] = t; }
+      float2* Zs = reinterpret_cast<float2*>(smem + L::O_Z) + st * NZ;
+      float2* Us = reinterpret_cast<float2*>(smem + L::O_U) + st * NU;
 
-    mbar_wait(&misc->full[st], (it >> 1) & 1);
-    if (warp == 0) {                                  // range check of the tile's samples (scaled by 2^14)
-      const float* mxs = reinterpret_cast<const float*>(smem + L::O_MAX) + st * LOAD_THREADS;
-      float m = fmaxf(fmaxf(mxs[lane], mxs[lane + 32]), fmaxf(mxs[lane + 64], mxs[lane + 96]));
+      // ---- two m-tiles per warp (the very last m-tile of the CTA tile is the look-ahead: features only) -----------------
+      const uint32_t sbase = smem_u32(smem + st * L::STAGE);
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-      if (lane == 0) misc->ok = (m < 65000.f && m >= 0.0625f) ? 1 : 0;
-    }
-
-    // ---- MMA phase: two m-tiles per warp (the very last m-tile of the CTA tile is the look-ahead: features only) ----------
-    const uint32_t sbase = smem_u32(smem + st * L::STAGE);
-    float u[2][2][4];                                 // [m-tile][n-tile][d0..d3]
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mt = 2 * warp + mi;
+        const bool main_tile = mt < MAIN_ROWS / 16;
+        const uint32_t abase = sbase + (uint32_t)((16 * mt + (lane & 15)) * S::SEGB + (lane >> 4) * 32);
+        float ah[2][4], al[2][4], fh[4], fl[4];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int mt = 2 * warp + mi;
-      const bool main_tile = mt < MAIN_ROWS / 16;
-      const uint32_t abase = sbase + (uint32_t)(((16 * mt + (lane & 15)) * S::PITCH + (lane >> 4) * 8) * 2);
-      float ah[2][4], al[2][4], fh[4], fl[4];
+        for (int i = 0; i < 4; ++i) { ah[0][i] = ah[1][i] = al[0][i] = al[1][i] = fh[i] = fl[i] = 0.f; }
+        if (main_tile) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { ah[0][i] = ah[1][i] = al[0][i] = al[1][i] = fh[i] = fl[i] = 0.f; }
-      if (main_tile) {
+          for (int k = 0; k < S::KS; ++k) {
+            const uint32_t ko = (uint32_t)((k / 5) * S::SEGB + (k % 5) * 64);
+            uint32_t xa[4], xl[4];
+            ldsm4(xa, abase + ko);
+            const bool need_lo = k >= S::LOA && k <= S::LOB;
+            if (need_lo) ldsm4(xl, abase + 16 + ko);
+            if (k >= S::HH0A && k <= S::HH0B) hmma(ah[0], xa, bf[k - S::HH0A]);
+            if (k >= S::HH1A && k <= S::HH1B) hmma(ah[1], xa, bf[S::O_HH1 + k - S::HH1A]);
+            if (k >= S::LO0A && k <= S::LO0B) { hmma(al[0], xa, bf[S::O_LO0 + k - S::LO0A]); hmma(al[0], xl, bf[k - S::HH0A]); }
+            if (k >= S::LO1A && k <= S::LO1B) { hmma(al[1], xa, bf[S::O_LO1 + k - S::LO1A]); hmma(al[1], xl, bf[S::O_HH1 + k - S::HH1A]); }
+            if (k >= S::FTA && k <= S::FTB) {
+              hmma(fh, xa, bf[S::O_FTH + k - S::FTA]);
+              hmma(fl, xa, bf[S::O_FTL + k - S::FTA]);
+              hmma(fl, xl, bf[S::O_FTH + k - S::FTA]);
+            }
+          }
+          // in-group symbols by symbol index: thread (g, q) holds symbols q and 4 + q of rows g and g + 8
 #pragma unroll
-        for (int k = 0; k < S::KS; ++k) {
-          const uint32_t ko = (uint32_t)(((k / 5) * S::PITCH + (k % 5) * 16) * 2);
-          uint32_t xa[4], xl[4];
-          ldsm4(xa, abase + ko);
-          const bool need_lo = k >= S::LOA && k <= S::LOB;
-          if (need_lo) ldsm4(xl, abase + L::ARR + ko);
-          if (k >= S::HH0A && k <= S::HH0B) hmma(ah[0], xa, bf[k - S::HH0A]);
-          if (k >= S::HH1A && k <= S::HH1B) hmma(ah[1], xa, bf[S::O_HH1 + k - S::HH1A]);
-          if (k >= S::LO0A && k <= S::LO0B) { hmma(al[0], xa, bf[S::O_LO0 + k - S::LO0A]); hmma(al[0], xl, bf[k - S::HH0A]); }
-          if (k >= S::LO1A && k <= S::LO1B) { hmma(al[1], xa, bf[S::O_LO1 + k - S::LO1A]); hmma(al[1], xl, bf[S::O_HH1 + k - S::HH1A]); }
-          if (k >= S::FTA && k <= S::FTB) {
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+            {
+              const int row = 16 * mt + g + 8 * h;          // symbol 8 row + 4 n + q = 16 (row / 2) + (8 (row & 1) + 4 n + q)
+              Us[(8 * (row & 1) + 4 * n + q) * US + (row >> 1)] = make_float2(ah[n][2 * h] + al[n][2 * h], ah[n][2 * h + 1] + al[n][2 * h + 1]);
+            }
+        } else {
+#pragma unroll
+          for (int k = S::FTA; k <= S::FTB; ++k) {
+            const uint32_t ko = (uint32_t)((k / 5) * S::SEGB + (k % 5) * 64);
+            uint32_t xa[4], xl[4];
+            ldsm4(xa, abase + ko);
+            ldsm4(xl, abase + 16 + ko);
             hmma(fh, xa, bf[S::O_FTH + k - S::FTA]);
             hmma(fl, xa, bf[S::O_FTL + k - S::FTA]);
             hmma(fl, xl, bf[S::O_FTH + k - S::FTA]);
           }
         }
-      } else {
-#pragma unroll
-        for (int k = S::FTA; k <= S::FTB; ++k) {
-          const uint32_t ko = (uint32_t)(((k / 5) * S::PITCH + (k % 5) * 16) * 2);
-          uint32_t xa[4], xl[4];
-          ldsm4(xa, abase + ko);
-          ldsm4(xl, abase + L::ARR + ko);
-          hmma(fh, xa, bf[S::O_FTH + k - S::FTA]);
-          hmma(fl, xa, bf[S::O_FTL + k - S::FTA]);
-          hmma(fl, xl, bf[S::O_FTH + k - S::FTA]);
-        }
+        // group features: thread (g, q) holds feature q (Zf0, Zb0, Zf1, Zb1) of rows g and g + 8
+        Zs[q * ZS + 16 * mt + g] = make_float2(fh[0] + fl[0], fh[1] + fl[1]);
+        Zs[q * ZS + 16 * mt + g + 8] = make_float2(fh[2] + fl[2], fh[3] + fl[3]);
       }
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) u[mi][n][i] = ah[n][i] + al[n][i];
-      // group features: thread (g, q) holds feature q (Zf0, Zb0, Zf1, Zb1) of rows g and g + 8
-      Zs[(16 * mt + g) * 4 + q] = make_float2(fh[0] + fl[0], fh[1] + fl[1]);
-      Zs[(16 * mt + g + 8) * 4 + q] = make_float2(fh[2] + fl[2], fh[3] + fl[3]);
+      __syncwarp();
+      tr_mark(a, it, 2, tid == 0);
+      if (lane == 0) { mbar_arrive(&misc->empty[st]); mbar_arrive(&misc->ufull[st]); }   // stage free for the loaders, symbols ready for the post warps
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&misc->empty[st]);      // this warp no longer reads the sample stage
-    bar_mma();
+    return;
+  }
 
-    // ---- group scan: thread r <-> row r.  F[r+1] = lam F[r] + Zf[r] (F[0] = carry);  Bk[r] = Zb[r+1] + lam Bk[r+1] (Bk[255] = 0) ----
-    {
-      const int r = tid;
-      const float4 z01 = *reinterpret_cast<const float4*>(&Zs[r * 4]), z23 = *reinterpret_cast<const float4*>(&Zs[r * 4 + 2]);
-      // inclusive scans: forward over Zf (value at r = state entering row r+1), backward over Zb (value at r = Zb[r] + lam * ...)
-      float2 v[4] = {make_float2(z01.x, z01.y), make_float2(z23.x, z23.y), make_float2(z01.z, z01.w), make_float2(z23.z, z23.w)};   // Zf0, Zf1, Zb0, Zb1
+  // ===================================================== post warps ======================================================
+  // thread p <-> rows 2p, 2p + 1 of the tile = symbols 16p .. 16p + 15: group scan of the slow-pole states (registers), the
+  // out-of-group sources added to the symbols, differential decisions -- one 32-bit word of DQPSK bits per thread
+  setmaxnreg_dec<96>();
+  {
+    const int p = (int)threadIdx.x - LOAD_THREADS - MMA_THREADS, warp = p >> 5;
+    uint64_t prev_off = ~0ull;
+    int prev_d0 = 0;
+    for (uint32_t it = 0;; ++it) {
+      const int st = it & 1;
+      tr_mark(a, it, 3, p == 0);
+      mbar_wait(&misc->ufull[st], (it >> 1) & 1);
+      tr_mark(a, it, 4, p == 0);
+      const uint32_t t = misc->tile_u[st];
+      if (t == ~0u) break;
+      const PskTile pl = a.tiles[t];
+      const bool chained = (pl.off == prev_off) && (pl.d0 == prev_d0 + TILE_SYMS);   // forward state carried from the previous tile
+      prev_off = pl.off; prev_d0 = pl.d0;
+      // ---- forward slow-pole state at the tile's first group when it cannot be carried: direct sum over the previous wlen
+      // samples (exact start-up state of scipy's filtfilt when the record start is within reach; psk_v2.cu has the algebra)
+      if (!chained) {                                   // uniform over the post warps
+        const int64_t n_d0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS;
+        const bool near_left = (n_d0 - a.wlen) <= (int64_t)a.n0;
+        const int cnt = (int)min((int64_t)a.wlen, n_d0 - (near_left ? (int64_t)a.n0 : (int64_t)0));
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+        for (int k0 = 1 + p; k0 <= cnt; k0 += 8 * POST_THREADS) {       // 8 independent loads in flight per thread
+          float xs[8];
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
+          for (int j = 0; j < 8; ++j) { const int k = k0 + j * POST_THREADS; xs[j] = k <= cnt ? load_sample<TIn>(a.samples, pl.off + (uint64_t)(n_d0 - k)) : 0.f; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = __ldg(&a.slow_pw4[min(k0 + j * POST_THREADS, a.wpad - 1)]);
+            s0.x = fmaf(xs[j], w.x, s0.x); s0.y = fmaf(xs[j], w.y, s0.y); s1.x = fmaf(xs[j], w.z, s1.x); s1.y = fmaf(xs[j], w.w, s1.y);
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, off); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, off);
+          s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+        }
+        if (lane == 0) { misc->tot[warp][0] = s0; misc->tot[warp][1] = s1; }
+        bar_post();
+        if (warp == 0 && lane < 2) {
+          float2 sum = make_float2(0.f, 0.f);
+          for (int w = 0; w < POST_WARPS; ++w) { sum.x += misc->tot[w][lane].x; sum.y += misc->tot[w][lane].y; }
+          if (near_left) {
+            // F[0] = sum_{n < n0} p^(n0-n) xL[n], xL = scipy's odd extension (pad_bp samples), then the constant xL[-pad_bp] for ever
+            const double pr = a.slow_p[2 * lane], pi = a.slow_p[2 * lane + 1];
+            const double x0 = load_sample_d<TIn>(a.samples, pl.off);
+            const double cr = 2.0 * x0 - load_sample_d<TIn>(a.samples, pl.off + a.pad_bp);
+            const double den = (1.0 - pr) * (1.0 - pr) + pi * pi;
+            double sr = cr * (1.0 - pr) / den, si = cr * pi / den;
+            for (int n = -a.pad_bp; n < a.n0; ++n) {
+              const double xv = (n < 0) ? 2.0 * x0 - load_sample_d<TIn>(a.samples, pl.off + (uint64_t)(-n)) : load_sample_d<TIn>(a.samples, pl.off + (uint64_t)n);
+              const double tr = pr * sr - pi * si + xv, ti = pr * si + pi * sr;
+              sr = tr; si = ti;
+            }
+            const double fr = pr * sr - pi * si, fi = pr * si + pi * sr;        // Fst[0] = p * s
+            const float4 pw4 = __ldg(&a.slow_pw4[(int)(n_d0 - a.n0)]);
+            const float2 pw = lane == 0 ? make_float2(pw4.x, pw4.y) : make_float2(pw4.z, pw4.w);
+            const float2 add = cmulf(pw, make_float2((float)fr, (float)fi));
+            sum.x += add.x; sum.y += add.y;
+          }
+          misc->carry[it & 1][lane] = make_float2(sum.x * a.state_scale, sum.y * a.state_scale);
+        }
+        bar_post();                                       // tot is reused by the scan below
+      }
+      const float2* Zs = reinterpret_cast<const float2*>(smem + L::O_Z) + st * NZ;
+      const float2* Us = reinterpret_cast<const float2*>(smem + L::O_U) + st * NU;
+      const int okv = misc->ok[st];
+
+      // ---- group scan, two rows per thread.  F[r+1] = lam F[r] + Zf[r] (F[0] = carry);  Bk[r] = Zb[r+1] + lam Bk[r+1] (Bk[255] = 0) ----
+      // features Zf0, Zb0, Zf1, Zb1 (f = 0..3) of rows 2p (a) and 2p + 1 (b): one 16-byte load per feature
+      const float4 q0 = *reinterpret_cast<const float4*>(&Zs[0 * ZS + 2 * p]), q1 = *reinterpret_cast<const float4*>(&Zs[1 * ZS + 2 * p]);
+      const float4 q2 = *reinterpret_cast<const float4*>(&Zs[2 * ZS + 2 * p]), q3 = *reinterpret_cast<const float4*>(&Zs[3 * ZS + 2 * p]);
+      const float2 zfa[2] = {make_float2(q0.x, q0.y), make_float2(q2.x, q2.y)}, zba[2] = {make_float2(q1.x, q1.y), make_float2(q3.x, q3.y)};
+      const float2 zfb[2] = {make_float2(q0.z, q0.w), make_float2(q2.z, q2.w)}, zbb[2] = {make_float2(q1.z, q1.w), make_float2(q3.z, q3.w)};
+      float2 v[4];                                      // thread totals: forward (pole 0, 1): lam a + b;  backward: a + lam b
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { v[i] = cfmaf(a.lam_pow[i][0], zfa[i], zfb[i]); v[2 + i] = cfmaf(a.lam_pow[i][0], zbb[i], zba[i]); }
+#pragma unroll
+      for (int sft = 0; sft < 5; ++sft) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 mm = a.lam_pow[k & 1][s];
+          const float2 mm = a.lam_pow[k & 1][sft + 1];  // (lam^2)^(2^sft)
           if (k < 2) {
-            const float ox = __shfl_up_sync(0xffffffffu, v[k].x, 1 << s), oy = __shfl_up_sync(0xffffffffu, v[k].y, 1 << s);
-            if (lane >= (1 << s)) v[k] = cfmaf(mm, make_float2(ox, oy), v[k]);
+            const float ox = __shfl_up_sync(0xffffffffu, v[k].x, 1 << sft), oy = __shfl_up_sync(0xffffffffu, v[k].y, 1 << sft);
+            if (lane >= (1 << sft)) v[k] = cfmaf(mm, make_float2(ox, oy), v[k]);
           } else {
-            const float ox = __shfl_down_sync(0xffffffffu, v[k].x, 1 << s), oy = __shfl_down_sync(0xffffffffu, v[k].y, 1 << s);
-            if (lane + (1 << s) < 32) v[k] = cfmaf(mm, make_float2(ox, oy), v[k]);
+            const float ox = __shfl_down_sync(0xffffffffu, v[k].x, 1 << sft), oy = __shfl_down_sync(0xffffffffu, v[k].y, 1 << sft);
+            if (lane + (1 << sft) < 32) v[k] = cfmaf(mm, make_float2(ox, oy), v[k]);
           }
         }
       }
       if (lane == 31) { misc->tot[warp][0] = v[0]; misc->tot[warp][1] = v[1]; }
       if (lane == 0) { misc->tot[warp][2] = v[2]; misc->tot[warp][3] = v[3]; }
-      bar_mma();
-      // state entering this warp's 32 rows from the left (k < 2) / right (k >= 2)
-      float2 c = make_float2(0.f, 0.f);
+      bar_post();
+      float2 c = make_float2(0.f, 0.f);                 // state entering this warp's 64 rows from the left (k < 2) / right (k >= 2)
       if (lane < 4) {
         const int k = lane;
-        const float2 M = a.lam_pow[k & 1][5];         // lam^32
+        const float2 M = a.lam_pow[k & 1][6];           // lam^64
         if (k < 2) {
           c = misc->carry[it & 1][k];
           for (int w = 0; w < warp; ++w) c = cfmaf(M, c, misc->tot[w][k]);
         } else {
-          for (int w = MMA_WARPS - 1; w > warp; --w) c = cfmaf(M, c, misc->tot[w][k]);
+          for (int w = POST_WARPS - 1; w > warp; --w) c = cfmaf(M, c, misc->tot[w][k]);
         }
       }
-      float2 car[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) car[k] = make_float2(__shfl_sync(0xffffffffu, c.x, k), __shfl_sync(0xffffffffu, c.y, k));
-      // F[r] (state entering row r) = lam^lane * car + exclusive prefix;  Bk[r] (sources after row r) = lam^(31-lane) * car + exclusive suffix
-      float2 outv[4];
+      float2 Fa[2], Fb[2], Ba[2], Bb[2];                // states of rows a = 2p, b = 2p + 1, per pole
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        const float2 car = make_float2(__shfl_sync(0xffffffffu, c.x, k), __shfl_sync(0xffffffffu, c.y, k));
         float ex, ey;
         if (k < 2) { ex = __shfl_up_sync(0xffffffffu, v[k].x, 1); ey = __shfl_up_sync(0xffffffffu, v[k].y, 1); }
         else { ex = __shfl_down_sync(0xffffffffu, v[k].x, 1); ey = __shfl_down_sync(0xffffffffu, v[k].y, 1); }
         const bool has = (k < 2) ? lane > 0 : lane < 31;
         const float2 excl = has ? make_float2(ex, ey) : make_float2(0.f, 0.f);
-        // lam^n for n = lane (forward) or 31 - lane (backward), from the binary powers
-        const int n = (k < 2) ? lane : 31 - lane;
-        float2 pw = make_float2(1.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < 5; ++s) if (n & (1 << s)) pw = cmulf(pw, a.lam_pow[k & 1][s]);
-        outv[k] = cfmaf(pw, car[k], excl);
+        const float2 e = cfmaf(misc->lpow[k & 1][(k < 2) ? lane : 31 - lane], car, excl);
+        if (k < 2) { Fa[k] = e; Fb[k] = cfmaf(a.lam_pow[k][0], e, zfa[k]); }          // F[2p], F[2p+1] = lam F[2p] + Zf[2p]
+        else { Bb[k - 2] = e; Ba[k - 2] = cfmaf(a.lam_pow[k - 2][0], e, zbb[k - 2]); }  // Bk[2p+1], Bk[2p] = Zb[2p+1] + lam Bk[2p+1]
       }
-      // the forward state a chained next tile starts from: the state entering row ADV_ROWS
-      if (r == ADV_ROWS) { misc->carry[(it + 1) & 1][0] = outv[0]; misc->carry[(it + 1) & 1][1] = outv[1]; }
-      // in place: row r now holds F0, B0, F1, B1  (the order the epilogue maps expect)
-      *reinterpret_cast<float4*>(&Zs[r * 4]) = make_float4(outv[0].x, outv[0].y, outv[2].x, outv[2].y);
-      *reinterpret_cast<float4*>(&Zs[r * 4 + 2]) = make_float4(outv[1].x, outv[1].y, outv[3].x, outv[3].y);
-    }
-    bar_mma();
+      // the forward state a chained next tile starts from: the state entering row ADV_ROWS (an even row)
+      if (2 * p == ADV_ROWS) { misc->carry[(it + 1) & 1][0] = Fa[0]; misc->carry[(it + 1) & 1][1] = Fa[1]; }
 
-    // ---- symbols: in-group part (accumulators) + out-of-group sources through the states; to shared memory by symbol index ----
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int mt = 2 * warp + mi;
-      if (mt < MAIN_ROWS / 16) {
+      // ---- symbols of the two rows: in-group part + out-of-group sources through the states --------------------------------
+      float2 y[17];
+      if (p < MAIN_ROWS / 2) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int row = 16 * mt + g + 8 * h;
-          const float4 s01 = *reinterpret_cast<const float4*>(&Zs[row * 4]), s23 = *reinterpret_cast<const float4*>(&Zs[row * 4 + 2]);
-          const float2 F0 = make_float2(s01.x, s01.y), B0 = make_float2(s01.z, s01.w), F1 = make_float2(s23.x, s23.y), B1 = make_float2(s23.z, s23.w);
+          const float2 F0 = h ? Fb[0] : Fa[0], F1 = h ? Fb[1] : Fa[1], B0 = h ? Bb[0] : Ba[0], B1 = h ? Bb[1] : Ba[1];
 #pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            const int s = 4 * n + q;
-            float2 y = make_float2(u[mi][n][2 * h], u[mi][n][2 * h + 1]);
-            y = mapf(__ldg(&a.maps[(0 * 8 + s) * 2 + 0]), F0, y);
-            y = mapf(__ldg(&a.maps[(0 * 8 + s) * 2 + 1]), B0, y);
-            y = mapf(__ldg(&a.maps[(1 * 8 + s) * 2 + 0]), F1, y);
-            y = mapf(__ldg(&a.maps[(1 * 8 + s) * 2 + 1]), B1, y);
-            Us[row * 8 + s] = y;
+          for (int s = 0; s < 8; ++s) {
+            {
+              float2 yy = Us[(8 * h + s) * US + p];
+              yy = map2(misc->maps[(0 * 8 + s) * 2 + 0], F0, yy);
+              yy = map2(misc->maps[(0 * 8 + s) * 2 + 1], B0, yy);
+              yy = map2(misc->maps[(1 * 8 + s) * 2 + 0], F1, yy);
+              yy = map2(misc->maps[(1 * 8 + s) * 2 + 1], B1, yy);
+              y[8 * h + s] = yy;
+            }
           }
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = make_float2(0.f, 0.f);
       }
-    }
-    bar_mma();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&misc->uempty[st]);     // this warp no longer reads the handoff buffers
+      // first symbol of the next thread (across warps through shared memory)
+      if (lane == 0) misc->yex[warp] = y[0];
+      y[16] = make_float2(__shfl_down_sync(0xffffffffu, y[0].x, 1), __shfl_down_sync(0xffffffffu, y[0].y, 1));
+      bar_post();
+      if (lane == 31 && warp + 1 < POST_WARPS) y[16] = misc->yex[warp + 1];
 
-    // ---- differential decisions: thread e <-> symbols 8e .. 8e+7 of the tile (236 threads), words of 32 bits as in psk_v2.cu ----
-    {
-      const int e0 = tid * 8;
-      const int nd = pl.d1 - pl.d0;                   // multiple of 32, <= TILE_SYMS
-      uint32_t part = 0;
-      if (e0 < TILE_SYMS) {
-        float2 y[9];
+      // ---- differential decisions: symbols 16p .. 16p + 15 against their successors ------------------------------------
+      {
+        const int e0 = p * 16;
+        const int nd = pl.d1 - pl.d0;                   // multiple of 32, <= TILE_SYMS
+        uint32_t part = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 p = *reinterpret_cast<const float4*>(&Us[e0 + 2 * i]);
-          y[2 * i] = make_float2(p.x, p.y); y[2 * i + 1] = make_float2(p.z, p.w);
-        }
-        y[8] = Us[e0 + 8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float2 prev = y[i], cur = y[i + 1];
           // the products reach 2^60 in accumulator units: scale one factor down (a positive factor does not move the angle)
           const float cx = cur.x * 5.9604645e-8f, cy = cur.y * 5.9604645e-8f;
@@ -439,19 +606,17 @@ __global__ void __launch_bounds__(MMA_THREADS + LOAD_THREADS, 1) psk_mma_kernel(
             part = (part << 1) | (dr < 0.f ? 1u : 0u);
           }
         }
+        if (a.bps == 2) {
+          if (e0 < nd && e0 < TILE_SYMS && okv) a.bits[pl.word_off + (uint64_t)((pl.d0 + e0) >> 4)] = __byte_perm(part, 0, 0x0123);
+        } else {
+          const uint32_t other = __shfl_down_sync(0xffffffffu, part, 1);
+          if ((lane & 1) == 0 && e0 < nd && e0 < TILE_SYMS && okv) a.bits[pl.word_off + (uint64_t)((pl.d0 + e0) >> 5)] = __byte_perm((part << 16) | other, 0, 0x0123);
+        }
+        if (p == 0 && !okv) a.redo_list[atomicAdd(a.redo_count, 1u)] = t;
       }
-      if (a.bps == 2) {
-        const uint32_t other = __shfl_down_sync(0xffffffffu, part, 1);
-        if ((lane & 1) == 0 && e0 < nd && misc->ok) a.bits[pl.word_off + (uint64_t)((pl.d0 + e0) >> 4)] = __byte_perm((part << 16) | other, 0, 0x0123);
-      } else {
-        uint32_t wv = part << (24 - 8 * (lane & 3));
-        wv |= __shfl_xor_sync(0xffffffffu, wv, 1);
-        wv |= __shfl_xor_sync(0xffffffffu, wv, 2);
-        if ((lane & 3) == 0 && e0 < nd && misc->ok) a.bits[pl.word_off + (uint64_t)((pl.d0 + e0) >> 5)] = __byte_perm(wv, 0, 0x0123);
-      }
-      if (tid == 0 && !misc->ok) a.redo_list[atomicAdd(a.redo_count, 1u)] = t;
+      tr_mark(a, it, 5, p == 0);
+      bar_post();                                        // tot / yex / carry are rewritten by the next tile
     }
-    // the next tile's barriers order every reuse of Zs / Us / misc against the reads above
   }
 }
 
@@ -467,7 +632,7 @@ struct MmaTables {
   std::vector<uint2> frags;        // [8][NFRAG][32]
   std::vector<float4> maps;        // [2][8][2]
   std::vector<float4> pw4;         // {p0^k, p1^k}
-  float2 lam[2], lam_pow[2][6];
+  float2 lam[2], lam_pow[2][7];
   float state_scale = 0.f;
   int wlen = 0;
   void* d_blob = nullptr;          // device copy: frags | maps | pw4
@@ -585,7 +750,7 @@ static bool build_mma_tables(const fb_psk_design& d, const float* taps, MmaTable
     const cd lam = cpow_(p[i], gs);
     T.lam[i] = make_float2((float)lam.r, (float)lam.i);
     cd x = lam;
-    for (int s = 0; s < 6; ++s) { T.lam_pow[i][s] = make_float2((float)x.r, (float)x.i); x = cmul_(x, x); }
+    for (int s = 0; s < 7; ++s) { T.lam_pow[i][s] = make_float2((float)x.r, (float)x.i); x = cmul_(x, x); }
   }
   T.wlen = d.wcols * sps;
   const int wpad = T.wlen + 2 + std::max(T.wlen, 4096);
@@ -651,6 +816,14 @@ bool fb_psk_mma_usable(fb_handle* h, const fb_psk_design& d, const float* taps) 
 
 int fb_psk_mma_tile_syms() { return TILE_SYMS; }
 
+// Experiments only: clock64 stamps of the last traced launch, [sm_count][TR_TILES][16]; returns TR_TILES (0 when not traced).
+extern "C" int fb_debug_mma_trace(fb_handle* h, long long* out, int n_ctas) {
+  if (!h || !h->mma_trace.p || !out) return 0;
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(out, h->mma_trace.p, (size_t)std::min(n_ctas, h->sm_count) * TR_TILES * 16 * 8, cudaMemcpyDeviceToHost);
+  return TR_TILES;
+}
+
 // Launches the tensor-core kernel over `n_tiles` tile descriptors (tile size TILE_SYMS).  redo: device buffer of
 // 1 + n_tiles uint32 (count, then the tiles the fp32 kernel must evaluate); the count is zeroed here.
 int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, const void* d_samples, int dtype, const PskTile* d_tiles,
@@ -665,19 +838,26 @@ int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, c
   a.wpad = (int)T->pw4.size(); a.wlen = T->wlen; a.n0 = d.n0; a.pad_bp = d.pad_bp; a.bps = d.bits_per_sym;
   for (int i = 0; i < 2; ++i) {
     a.lam[i] = T->lam[i];
-    for (int s = 0; s < 6; ++s) a.lam_pow[i][s] = T->lam_pow[i][s];
+    for (int s = 0; s < 7; ++s) a.lam_pow[i][s] = T->lam_pow[i][s];
     a.slow_p[2 * i] = d.slow_p[2 * i]; a.slow_p[2 * i + 1] = d.slow_p[2 * i + 1];
   }
   a.state_scale = T->state_scale;
   a.rho = make_float2(d.rho[0], d.rho[1]);
-  a.bits = d_bits; a.redo_count = d_redo; a.redo_list = d_redo + 1;
-  FB_CUDA(h, cudaMemsetAsync(d_redo, 0, 4, h->stream));
+  a.bits = d_bits; a.redo_count = d_redo; a.chunk_ctr = d_redo + 1; a.redo_list = d_redo + 2;
+  if (const char* e = getenv("FB_MMA_DBG")) a.dbg = atoi(e);
+  if (getenv("FB_MMA_TRACE")) {
+    int rc2 = fb_ensure(h, h->mma_trace, (size_t)h->sm_count * TR_TILES * 16 * 8);
+    if (rc2) return rc2;
+    FB_CUDA(h, cudaMemsetAsync(h->mma_trace.p, 0, (size_t)h->sm_count * TR_TILES * 16 * 8, h->stream));
+    a.trace = (long long*)h->mma_trace.p;
+  }
+  FB_CUDA(h, cudaMemsetAsync(d_redo, 0, 8, h->stream));
   const int smem = Smem<S>::TOTAL;
   const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
 #define FB_MMA_LAUNCH(TIN)                                                                                              \
   do {                                                                                                                  \
     FB_CUDA(h, cudaFuncSetAttribute(psk_mma_kernel<TIN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-    psk_mma_kernel<TIN, S><<<grid, MMA_THREADS + LOAD_THREADS, smem, h->stream>>>(a);                                   \
+    psk_mma_kernel<TIN, S><<<grid, ALL_THREADS, smem, h->stream>>>(a);                                   \
   } while (0)
   if (dtype == FB_F32) FB_MMA_LAUNCH(float);
   else if (dtype == FB_F64) FB_MMA_LAUNCH(double);

@@ -147,7 +147,7 @@ extern "C" int fb_debug_pm_trace(unsigned long long* t, unsigned int* sm) {
 __device__ __forceinline__ void pm_mark(int) {}
 #endif
 
-template <typename TIn, int NT, int SPS, int PP, int NSL>
+template <typename TIn, int NT, int SPS, int PP, int NSL, bool REDO>
 __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __grid_constant__ PskMainArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float2 s_bnd[2][2][4][2];   // boundary-state partial sums [pair][dir][slice][pole of the pair]
@@ -163,9 +163,12 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
   pm_mark(0);
   for (int i = threadIdx.x; i < nslow * SLOW_TBL; i += blockDim.x) s_tbl[i] = __ldg(&a.slow_tbl[i]);   // visible after the staging barrier
   // ---- this CTA's tile(s): blockIdx.x, or -- in redo mode -- a stride over the redo list ---------------------------------------
-  const uint32_t n_work = a.redo ? __ldg(&a.redo[0]) : a.n_tiles;
-  for (uint32_t work = blockIdx.x; work < n_work; work += a.redo ? gridDim.x : n_work) {
-  const uint32_t tile = a.redo ? __ldg(&a.redo[1 + work]) : work;
+  // (REDO is a template flag so that the plain one-tile-per-CTA build keeps its register allocation)
+  const uint32_t n_work = REDO ? __ldg(&a.redo[0]) : a.n_tiles;      // redo: [0] count, [1] scheduler counter of psk_mma.cu, [2..] tiles
+  uint32_t work = blockIdx.x;
+  if (REDO && work >= n_work) return;
+  do {
+  const uint32_t tile = REDO ? __ldg(&a.redo[2 + work]) : work;
   auto get_tile = [&](uint32_t t) {
     PskTile q;
     if (a.uni_tpr) {
@@ -605,8 +608,8 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
     }
   }
   pm_mark(6);
-  if (a.redo) __syncthreads();                          // the next tile of the list reuses the shared arrays
-  }
+  if (REDO) __syncthreads();                            // the next tile of the list reuses the shared arrays
+  } while (REDO && (work += gridDim.x) < n_work);
 }
 
 // =====================================================================================================
@@ -844,7 +847,11 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-  if (ea.n_jobs > 0) {
+  if (ea.n_jobs > 0 && !getenv("FB_PSK_NO_EDGE")) {      // (the knob is for timing experiments only: the record edges stay undecided)
+    // The edge kernel runs beside the interior kernel, whose CTAs need (nearly) all of an SM's shared memory: ask for the
+    // same L1 / shared-memory split, otherwise an SM that hosts an edge CTA must drain before it can be re-configured and the
+    // interior CTA placed there starts ~2 ms late (the length of the edge kernel).
+    FB_CUDA(h, cudaFuncSetAttribute(psk_edge_kernel<TIn>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     psk_edge_kernel<TIn><<<(ea.n_jobs + 31) / 32, 32, 0, h->stream2>>>(ea);
     h->launches++;
   }
@@ -863,18 +870,22 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
   if (n_tiles > 0) {
     if (h->profiling && !use_mma) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
     const int ntv = ma.nt == ma.ntp ? ma.nt : 0;
-#define FB_LAUNCH_MAIN(NTV, SPSV, PPV, NSLV)                                                                                              \
-    do {                                                                                                                                \
-      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV><<<grid, nthreads, smem, h->stream>>>(ma);                                                  \
+#define FB_LAUNCH_MAIN(NTV, SPSV, PPV, NSLV, REDOV)                                                                                              \
+    do {                                                                                                                                       \
+      FB_CUDA(h, cudaFuncSetAttribute(psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV, REDOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      psk_main_kernel<TIn, NTV, SPSV, PPV, NSLV, REDOV><<<grid, nthreads, smem, h->stream>>>(ma);                                                  \
     } while (0)
-    if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
-    else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0);
-    else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0);
-    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0, 0);
-    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0, 0);
-    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0, 0);
-    else FB_LAUNCH_MAIN(0, 0, 0, 0);
+    if (ma.redo) {
+      if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0, true);           // the class psk_mma.cu serves
+      else return FB_EINVAL;
+    }
+    else if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2, false);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
+    else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0, false);
+    else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0, false);
+    else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0, 0, false);
+    else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0, 0, false);
+    else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0, 0, false);
+    else FB_LAUNCH_MAIN(0, 0, 0, 0, false);
 #undef FB_LAUNCH_MAIN
     if (h->profiling && !use_mma) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     h->launches++;
@@ -1104,7 +1115,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
     if ((rc = fb_ensure(h, h->tiles, (size_t)std::max<uint32_t>(1, n_tiles) * sizeof(PskTile)))) return rc;
-    if (use_mma && (rc = fb_ensure(h, h->redo, ((size_t)n_tiles + 2) * 4))) return rc;
+    if (use_mma && (rc = fb_ensure(h, h->redo, ((size_t)n_tiles + 4) * 4))) return rc;
     if (n_tiles > 0) {
       psk_tiles_kernel<<<(n_tiles + 255) / 256, 256, 0, h->stream>>>((const RecPlan*)h->plans.p, (const uint32_t*)h->tile_first.p, n_rec,
                                                                       n_tiles, T, (PskTile*)h->tiles.p);
