@@ -18,9 +18,11 @@
 #include "common.cuh"
 #include "psk_shared.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
+#include <utility>
 
 namespace {
 
@@ -70,6 +72,8 @@ struct MmaArgs {
   uint32_t* redo_list;
   uint32_t* chunk_ctr;          // dynamic scheduling: CTAs claim chunks of CHUNK consecutive tiles
   long long* trace;             // FB_MMA_TRACE: [CTA][TR_TILES][16] clock64 stamps of the phase boundaries (experiments only)
+  float4 maps_c[2 * 8 * 2];     // `maps` rearranged for packed FMAs {m.x, m.z, m.y, m.w}: constant-bank operands of the post warps
+  uint32_t tm_rows;             // rows of the tensor map over the sample buffer (0: no TMA, every tile through the guarded loads)
   int dbg;                      // timing experiments only (FB_MMA_DBG): 1 = loaders skip their work, 2 = MMA warps skip theirs, 4 = no epilogue
 };
 
@@ -85,6 +89,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
       ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Hand-off barriers between the roles: hardware named barriers (bar.arrive by the producers, bar.sync by the consumers), so that
+// a waiting warp costs no issue slots and no shared-memory traffic (polling mbarriers took 47 % of the executed instructions).
+// Each barrier is used once per tile and stage, producers + consumers threads; ids 4 .. 9 (0: __syncthreads, 2: post, 3: loaders).
+constexpr int HB_FULL = 4, HB_UFULL = 6, HB_UEMPTY = 8;
+__device__ __forceinline__ void hb_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(384) : "memory"); }
+__device__ __forceinline__ void hb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(384) : "memory"); }
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
@@ -160,59 +175,64 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 constexpr int POST_WARPS = 4, POST_THREADS = 32 * POST_WARPS;
-constexpr int ALL_THREADS = LOAD_THREADS + MMA_THREADS + POST_THREADS;          // 512: warps 0-3 load, 4-11 MMA, 12-15 post
+constexpr int NQ = 4, QROWS = 64, QBOX = 66;   // a stage lands as NQ TMA boxes of QBOX segments, QROWS apart (SEGS = 3 * 64 + 66)
+static_assert((NQ - 1) * QROWS + QBOX == SEGS, "landing boxes must cover the stage exactly");
+constexpr int ALL_THREADS = LOAD_THREADS + MMA_THREADS + POST_THREADS;          // 512: warps 0-3 convert, 4-11 MMA, 12-15 post (post warp 0 also fetches)
 // Handoff buffers MMA warps -> post warps, laid out for the READER (post thread p owns symbols 16p .. 16p+15 = rows 2p, 2p+1):
 //   U[j][p] (stride US): symbol 16p + j;   Z[f][row] (stride ZS): feature f of a row  -- reads are conflict-free, writes 2-way
 constexpr int US = 121, NU = 16 * US, ZS = 264, NZ = 4 * ZS;
 
 template <typename S> struct Smem {
-  static constexpr int STAGE = SEGS * S::SEGB;             // bytes of one sample stage
+  static constexpr int STAGE = (SEGS * S::SEGB + 127) / 128 * 128;   // bytes of one sample stage (TMA destinations are 128-byte aligned)
   static constexpr int O_Z = 2 * STAGE;                    // float2 [2][ROWS][4]: group features per tile parity
   static constexpr int O_U = O_Z + 2 * NZ * 8;             // float2 [2][NU]: in-group symbols (accumulator units) per tile parity
   static constexpr int O_MAX = O_U + 2 * NU * 8;           // float [2][LOAD_THREADS]
-  static constexpr int O_MISC = O_MAX + 2 * LOAD_THREADS * 4;
-  static constexpr int TOTAL = O_MISC + 1792;
+  static constexpr int O_MISC = O_MAX + 2 * LOAD_THREADS * 4;   // (only 2 x LOAD_WARPS floats of the slot are in use)
+  static constexpr int TOTAL = O_MISC + 1792 + 128;        // + slack to align the base
 };
 
 struct Misc {
-  float4 maps[2 * 8 * 2];        // MmaArgs::maps rearranged for packed FMAs: {m.x, m.z, m.y, m.w}
   float2 lpow[2][32];            // lam^(2n), n = 0..31, per pole: two rows per post thread
   float2 tot[POST_WARPS][4];     // warp totals of the group scan
   float2 carry[2][2];            // [tile parity][pole]: forward states entering row 0 (written by the previous tile at its row ADV_ROWS)
   float2 yex[POST_WARPS + 1];    // first symbol of every post warp (differential across warp edges)
   int ok[2];                     // [tile parity]: the tile's samples fit the fp16 split
   uint32_t tile_s[2], tile_u[2]; // tile index travelling with the sample stage / with the handoff buffers (~0u: no more work)
-  uint32_t chunk;                // the loaders' current chunk
-  uint64_t raw[2];               // sample stages: TMA bytes landed
-  uint64_t full[2], empty[2];    // sample stages: converted by the loaders -> MMA warps
-  uint64_t ufull[2], uempty[2];  // symbol / feature buffers: MMA warps -> post warps
+  PskTile pl_s[2], pl_u[2];      // ... and its descriptor (one global load per tile, by the loaders)
+  int inb_s[2];                  // the stage is filled by TMA (raw fp32, tile inside its recording); 0: guarded loads by the converters
+  uint64_t raw[2][NQ];           // sample stages: bytes of a landing sub-block (TMA, complete_tx)
 };
 
+static_assert(sizeof(Misc) <= 1792, "Misc outgrew its shared-memory slot");
 __device__ __forceinline__ void bar_post() { asm volatile("bar.sync 2, %0;" ::"n"(POST_THREADS) : "memory"); }
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 // acc + f.x * (m.x, m.y) + f.y * (m.z, m.w): one real 2x2 map of a complex state as two packed FMAs
 __device__ __forceinline__ float2 map2(float4 m, float2 f, float2 acc) {
   return ffma2(make_float2(f.y, f.y), make_float2(m.z, m.w), ffma2(make_float2(f.x, f.x), make_float2(m.x, m.y), acc));
 }
+template <typename F, int... I> __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, typename F> __device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // 120 registers per thread at launch (61 440 of the SM's 65 536: the float64 edge kernel's 32-thread CTAs still fit beside a
-// resident CTA of this kernel); the roles then re-balance: loaders 48, MMA warps 168, post warps 96.
+// resident CTA of this kernel); the roles then re-balance per scheduler (one loader, two MMA, one post warp each): 48 + 2 x 168 + 96.
 template <typename TIn, typename S>
-__global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   using L = Smem<S>;
   Misc* misc = reinterpret_cast<Misc*>(smem + L::O_MISC);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&misc->raw[i], 1); mbar_init(&misc->full[i], LOAD_THREADS); mbar_init(&misc->empty[i], MMA_WARPS);
-      mbar_init(&misc->ufull[i], MMA_WARPS); mbar_init(&misc->uempty[i], POST_WARPS);
+      for (int q = 0; q < NQ; ++q) mbar_init(&misc->raw[i][q], 1);
+
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 32) { const float4 m = __ldg(&a.maps[threadIdx.x]); misc->maps[threadIdx.x] = make_float4(m.x, m.z, m.y, m.w); }
   if (threadIdx.x >= 64 && threadIdx.x < 128) {         // lam^(2n) by binary powers
     const int i = ((int)threadIdx.x - 64) >> 5, n = 2 * (threadIdx.x & 31);
     float2 pw = make_float2(1.f, 0.f);
@@ -228,64 +248,35 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
   if (wid < LOAD_WARPS) {
     setmaxnreg_dec<48>();
     // ================================================== loader warps ==================================================
-    // One elected thread brings the tile's samples in with bulk asynchronous copies (one per 80-sample segment, 320 bytes:
-    // no registers, no load instructions, the whole tile in flight at once); all loader threads then convert the slots in
-    // place.  120 of the 128 threads: thread lt = 10 rg + c owns slot c of segments rg, rg + 12, rg + 24, ... (immediates).
+    // A tile's samples arrive by TMA (requested by the first thread of the post warps, see there), four boxes, each
+    // completing its own mbarrier.  120 converter threads rewrite the landed slots in place, [8 x fp32] -> [8 x fp16 hi |
+    // 8 x fp16 lo] (x 2^14; 22 significant bits): thread lt = 10 rg + c owns slot c of segments rg, rg + 12, ...  Tiles at the
+    // ends of a recording and other sample types come through guarded loads instead.
     const int lt = (int)threadIdx.x;
     constexpr int UPS = S::SEG / 8, LROWS = 12, NIT = (SEGS + LROWS - 1) / LROWS;
     const bool lactive = lt < UPS * LROWS;
     const int rg = lt / UPS, c = lt - rg * UPS;
-    uint32_t t = 0, t_end = 0;
     for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
+      const uint32_t par = (it >> 1) & 1;
       tr_mark(a, it, 10, lt == 0);
-      if (t == t_end) {                                  // claim the next chunk (one atomic per CHUNK tiles)
-        asm volatile("bar.sync 3, %0;" ::"n"(LOAD_THREADS) : "memory");      // everybody has read the previous value
-        if (lt == 0) misc->chunk = atomicAdd(a.chunk_ctr, 1u);
-        asm volatile("bar.sync 3, %0;" ::"n"(LOAD_THREADS) : "memory");
-        const uint32_t ch = misc->chunk;
-        t = ch * CHUNK;
-        t_end = min(a.n_tiles, t + CHUNK);
-        if (ch >= (a.n_tiles + CHUNK - 1) / CHUNK) {     // no more work: pass the end marker down the pipeline
-          mbar_wait(&misc->empty[st], ((it >> 1) & 1) ^ 1);
-          if (lt == 0) misc->tile_s[st] = ~0u;
-          mbar_arrive(&misc->full[st]);
-          break;
-        }
-      }
-      const PskTile pl = a.tiles[t];
-      const int64_t N = (int64_t)pl.n;
-      // window origin of row 0, moved down to a multiple of 8 elements of the sample buffer
-      const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;     // H+ = 8 sps
-      const int sh = (int)((pl.off + (uint64_t)w0) & 7);
-      const int64_t w0a = w0 - sh;
-      unsigned char* stage = smem + st * L::STAGE;
-      unsigned char* sb = stage + rg * S::SEGB + c * 32;
-      const bool inb = sizeof(TIn) == 4 && w0a >= 0 && w0a + (int64_t)SEGS * S::SEG <= N;   // raw fp32 tiles go through the TMA path
-      float mx = 0.f;
-      mbar_wait(&misc->empty[st], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&misc->raw[st][0], par);
       tr_mark(a, it, 11, lt == 0);
+      if (misc->tile_s[st] == ~0u) { hb_arrive(HB_FULL + st); break; }
+      // ---- convert the current tile in place -----------------------------------------------------------------------------
+      unsigned char* sb = smem + st * L::STAGE + rg * S::SEGB + c * 32;
+      float mx = 0.f;
       if (a.dbg & 1) {
         mx = 1.f;
-      } else if (inb) {
-        // every thread copies exactly the slots it will convert: 16-byte asynchronous copies (no registers, all in flight at
-        // once), then only its own copies have to have landed
-        if (lactive) {
-          const char* src = reinterpret_cast<const char*>(a.samples) + (pl.off + (uint64_t)w0a + (uint64_t)lt * 8) * 4;
-          const uint32_t dst = smem_u32(sb);
 #pragma unroll
-          for (int item = 0; item < NIT; ++item) {
-            if (item == NIT - 1 && rg + LROWS * item >= SEGS) break;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + item * (LROWS * S::SEGB)), "l"(src + (size_t)item * (LROWS * S::SEG * 4)) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + item * (LROWS * S::SEGB) + 16), "l"(src + (size_t)item * (LROWS * S::SEG * 4) + 16) : "memory");
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (lactive) {
-#pragma unroll 2
-          for (int item = 0; item < NIT; ++item) {
-            if (item == NIT - 1 && rg + LROWS * item >= SEGS) break;
+        for (int q = 1; q < NQ; ++q) mbar_wait(&misc->raw[st][q], par);
+      } else if (misc->inb_s[st]) {
+        static_for<NIT>([&](auto I) {
+          constexpr int item = decltype(I)::value;
+          constexpr int q_now = (LROWS * item + LROWS - 1) / QROWS < NQ - 1 ? (LROWS * item + LROWS - 1) / QROWS : NQ - 1;
+          constexpr int q_before = item == 0 ? 0 : ((LROWS * item - 1) / QROWS < NQ - 1 ? (LROWS * item - 1) / QROWS : NQ - 1);
+          if (q_now != q_before) mbar_wait(&misc->raw[st][q_now], par);
+          if (lactive && !(item == NIT - 1 && rg + LROWS * item >= SEGS)) {
             unsigned char* q8 = sb + item * (LROWS * S::SEGB);
             const float4 r0 = *reinterpret_cast<const float4*>(q8), r1 = *reinterpret_cast<const float4*>(q8 + 16);
             const float2 k = make_float2(SX, SX);
@@ -297,19 +288,25 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
             *reinterpret_cast<uint4*>(q8) = hi;
             *reinterpret_cast<uint4*>(q8 + 16) = lo;
           }
-        }
-      } else if (lactive) {
-        for (int item = 0; item < NIT; ++item) {                  // tiles at the ends of a recording, and other sample types: guarded loads
+        });
+      } else {
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) mbar_wait(&misc->raw[st][q], par);     // (plain arrivals: keeps the phases in step)
+        const PskTile pl = misc->pl_s[st];
+        const int64_t c_N = (int64_t)pl.n;
+        const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;
+        const int64_t c_w0a = w0 - (int64_t)((pl.off + (uint64_t)w0) & 7);
+        for (int item = 0; item < NIT && lactive; ++item) {       // tiles at the ends of a recording, and other sample types: guarded loads
           if (rg + LROWS * item >= SEGS) break;
-          const int64_t n = w0a + (int64_t)lt * 8 + (int64_t)item * (LROWS * S::SEG);
+          const int64_t n = c_w0a + (int64_t)lt * 8 + (int64_t)item * (LROWS * S::SEG);
           float v[8];
-          if (n >= 0 && n + 8 <= N) {
+          if (n >= 0 && n + 8 <= c_N) {
             Raw8<TIn> r;
             r.load(a.samples, pl.off + (uint64_t)n);
             r.get(v);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (n + j >= 0 && n + j < N) ? load1s<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = (n + j >= 0 && n + j < c_N) ? load1s<TIn>(a.samples, pl.off + (uint64_t)(n + j)) : 0.f;
           }
           uint4 hi, lo;
           split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
@@ -319,11 +316,12 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
           *reinterpret_cast<uint4*>(sb + item * (LROWS * S::SEGB) + 16) = lo;
         }
       }
-      reinterpret_cast<float*>(smem + L::O_MAX)[st * LOAD_THREADS + lt] = mx;
-      if (lt == 0) misc->tile_s[st] = t;
+      {
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));   // non-negative floats order like their bit patterns
+        if (lane == 0) reinterpret_cast<uint32_t*>(smem + L::O_MAX)[st * LOAD_WARPS + wid] = wm;
+      }
       tr_mark(a, it, 12, lt == 0);
-      mbar_arrive(&misc->full[st]);
-      ++t;
+      hb_arrive(HB_FULL + st);
     }
     return;
   }
@@ -338,18 +336,17 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
     for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
       tr_mark(a, it, 0, tid == 0);
-      if (a.trace && tid == 0 && it < TR_TILES) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.trace[((size_t)blockIdx.x * TR_TILES + it) * 16 + 13] = gt; }
-      mbar_wait(&misc->full[st], (it >> 1) & 1);
+      hb_sync(HB_FULL + st);
       tr_mark(a, it, 1, tid == 0);
       const uint32_t t = misc->tile_s[st];
       if (t == ~0u) {                                    // end marker: forward it to the post warps
-        mbar_wait(&misc->uempty[st], ((it >> 1) & 1) ^ 1);
+        if (it >= 2) hb_sync(HB_UEMPTY + st);
         if (tid == 0) misc->tile_u[st] = ~0u;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&misc->ufull[st]);
+        hb_arrive(HB_UFULL + st);
         break;
       }
-      const PskTile pl = a.tiles[t];
+      const PskTile pl = misc->pl_s[st];
       const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;
       const int sh = (int)((pl.off + (uint64_t)w0) & 7);
       if (sh != cur_sh) {
@@ -358,18 +355,19 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         for (int i = 0; i < S::NFRAG; ++i) bf[i] = __ldg(src + i * 32);
         cur_sh = sh;
       }
-      if (a.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(&misc->empty[st]); continue; }
+      if (a.dbg & 2) { if (it >= 2) hb_sync(HB_UEMPTY + st); if (tid == 0) misc->tile_u[st] = t; __syncwarp(); hb_arrive(HB_UFULL + st); continue; }
       int okv = 1;
-      if (warp == 0) {                                  // range check of the tile's samples (scaled by 2^14)
-        const float* mxs = reinterpret_cast<const float*>(smem + L::O_MAX) + st * LOAD_THREADS;
-        float m = fmaxf(fmaxf(mxs[lane], mxs[lane + 32]), fmaxf(mxs[lane + 64], mxs[lane + 96]));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      if (tid == 0) {                                   // range check of the tile's samples (scaled by 2^14): one maximum per loader warp
+        const float4 mxs = *reinterpret_cast<const float4*>(smem + L::O_MAX + st * LOAD_WARPS * 4);
+        const float m = fmaxf(fmaxf(mxs.x, mxs.y), fmaxf(mxs.z, mxs.w));
         okv = (m < 65000.f && m >= 0.0625f) ? 1 : 0;
       }
+      tr_mark(a, it, 13, tid == 0);
       // the symbol / feature buffers of this parity must have been drained by the post warps (two tiles ago)
-      mbar_wait(&misc->uempty[st], ((it >> 1) & 1) ^ 1);
-      if (warp == 0 && lane == 0) { misc->ok[st] = okv; misc->tile_u[st] = t; }
+      if (it >= 2) hb_sync(HB_UEMPTY + st);
+      tr_mark(a, it, 14, tid == 0);
+      if (tid == 0) { misc->ok[st] = okv; misc->tile_u[st] = t; misc->pl_u[st] = pl; }
+      __syncwarp();                                     // (the waits above leave the lanes diverged; ldmatrix / mma are warp-collective)
       float2* Zs = reinterpret_cast<float2*>(smem + L::O_Z) + st * NZ;
       float2* Us = reinterpret_cast<float2*>(smem + L::O_U) + st * NU;
 
@@ -425,10 +423,11 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         // group features: thread (g, q) holds feature q (Zf0, Zb0, Zf1, Zb1) of rows g and g + 8
         Zs[q * ZS + 16 * mt + g] = make_float2(fh[0] + fl[0], fh[1] + fl[1]);
         Zs[q * ZS + 16 * mt + g + 8] = make_float2(fh[2] + fl[2], fh[3] + fl[3]);
+        if (mi == 0) tr_mark(a, it, 15, tid == 0);
       }
       __syncwarp();
       tr_mark(a, it, 2, tid == 0);
-      if (lane == 0) { mbar_arrive(&misc->empty[st]); mbar_arrive(&misc->ufull[st]); }   // stage free for the loaders, symbols ready for the post warps
+      hb_arrive(HB_UFULL + st);                          // stage free for the loaders, symbols ready for the post warps
     }
     return;
   }
@@ -439,16 +438,70 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
   setmaxnreg_dec<96>();
   {
     const int p = (int)threadIdx.x - LOAD_THREADS - MMA_THREADS, warp = p >> 5;
+    const int trp = (a.dbg >> 4) * 32;               // experiments: which post warp stamps the trace (FB_MMA_DBG = 16 w)
+    // ---- fetch (first post thread): claims tiles (chunks of CHUNK consecutive tiles from a global counter) and brings a tile's
+    // samples in with four TMA tile copies through a 2-D tensor map of the sample buffer whose rows are the 80-sample
+    // segments and whose box is 84 samples wide -- the 336-byte shared-memory pitch that keeps ldmatrix conflict-free comes
+    // for free, no load instruction is issued, nothing passes through registers or the LSU, the whole tile is in flight at
+    // once.  A stage is free the moment its tile's hand-off to the post warps completes (every MMA warp has read it), which
+    // is exactly when this thread wakes up for that tile: tile it + 2 is requested at the top of iteration it.
+    const uint32_t n_chunks = (a.n_tiles + CHUNK - 1) / CHUNK;
+    uint32_t f_t = 0, f_end = 0;
+    bool f_done = false, f_have = false;
+    PskTile f_pl{};
+    auto fetch = [&](int fs) {                           // thread p == 0 only; stage fs is free
+      if (f_t == f_end) {
+        const uint32_t ch = atomicAdd(a.chunk_ctr, 1u);
+        if (ch >= n_chunks) {                            // no more work: pass the end marker down the pipeline
+          misc->tile_s[fs] = ~0u;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) mbar_arrive(&misc->raw[fs][q]);
+          f_done = true;
+          return;
+        }
+        f_t = ch * CHUNK; f_end = min(a.n_tiles, f_t + CHUNK); f_have = false;
+      }
+      const uint32_t tc = f_t++;
+      const PskTile pl = f_have ? f_pl : a.tiles[tc];
+      // window origin of row 0, moved down to a multiple of 8 elements of the sample buffer
+      const int64_t w0 = (int64_t)a.n0 + (int64_t)pl.d0 * S::SPS - S::SPS * S::G;     // H+ = 8 sps
+      const int64_t w0a = w0 - (int64_t)((pl.off + (uint64_t)w0) & 7);
+      const uint64_t e0 = pl.off + (uint64_t)w0a;       // first element of the stage in the sample buffer
+      const uint32_t e8 = (uint32_t)(e0 >> 3);          // (e0 is a multiple of 8 and below 2^35: 32-bit arithmetic)
+      const uint32_t c1 = e8 / (S::SEG / 8), c0 = (e8 - c1 * (S::SEG / 8)) * 8;
+      const bool inb = sizeof(TIn) == 4 && w0a >= 0 && w0a + (int64_t)SEGS * S::SEG <= (int64_t)pl.n && (e0 >> 35) == 0 && (uint64_t)c1 + SEGS <= a.tm_rows && !(a.dbg & 1);
+      misc->tile_s[fs] = tc; misc->pl_s[fs] = pl; misc->inb_s[fs] = inb ? 1 : 0;
+      if (inb) {
+        // the stage was last written (converters) and read (ldmatrix) through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t dst = smem_u32(smem + fs * L::STAGE);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const uint32_t mb = smem_u32(&misc->raw[fs][q]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "n"(QBOX * S::SEGB) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(dst + q * (QROWS * S::SEGB)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1 + q * QROWS), "r"(mb) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mbar_arrive(&misc->raw[fs][q]);
+      }
+      f_have = f_t < f_end;
+      if (f_have) f_pl = a.tiles[f_t];                   // consumed by the next call: the load's latency stays off the critical path
+    };
+    if (p == 0) { fetch(0); if (!f_done) fetch(1); }
     uint64_t prev_off = ~0ull;
     int prev_d0 = 0;
     for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
-      tr_mark(a, it, 3, p == 0);
-      mbar_wait(&misc->ufull[st], (it >> 1) & 1);
-      tr_mark(a, it, 4, p == 0);
+      tr_mark(a, it, 3, p == trp);
+      hb_sync(HB_UFULL + st);
+      __syncwarp();                                     // the wait leaves the lanes diverged; the scan below is all warp shuffles
+      tr_mark(a, it, 4, p == trp);
       const uint32_t t = misc->tile_u[st];
       if (t == ~0u) break;
-      const PskTile pl = a.tiles[t];
+      if (p == 0 && !f_done) fetch(st);                  // stage st is free: request tile it + 2
+      const PskTile pl = misc->pl_u[st];
       const bool chained = (pl.off == prev_off) && (pl.d0 == prev_d0 + TILE_SYMS);   // forward state carried from the previous tile
       prev_off = pl.off; prev_d0 = pl.d0;
       // ---- forward slow-pole state at the tile's first group when it cannot be carried: direct sum over the previous wlen
@@ -529,7 +582,9 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
       }
       if (lane == 31) { misc->tot[warp][0] = v[0]; misc->tot[warp][1] = v[1]; }
       if (lane == 0) { misc->tot[warp][2] = v[2]; misc->tot[warp][3] = v[3]; }
+      tr_mark(a, it, 6, p == trp);
       bar_post();
+      tr_mark(a, it, 7, p == trp);
       float2 c = make_float2(0.f, 0.f);                 // state entering this warp's 64 rows from the left (k < 2) / right (k >= 2)
       if (lane < 4) {
         const int k = lane;
@@ -567,10 +622,10 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
           for (int s = 0; s < 8; ++s) {
             {
               float2 yy = Us[(8 * h + s) * US + p];
-              yy = map2(misc->maps[(0 * 8 + s) * 2 + 0], F0, yy);
-              yy = map2(misc->maps[(0 * 8 + s) * 2 + 1], B0, yy);
-              yy = map2(misc->maps[(1 * 8 + s) * 2 + 0], F1, yy);
-              yy = map2(misc->maps[(1 * 8 + s) * 2 + 1], B1, yy);
+              yy = map2(a.maps_c[(0 * 8 + s) * 2 + 0], F0, yy);
+              yy = map2(a.maps_c[(0 * 8 + s) * 2 + 1], B0, yy);
+              yy = map2(a.maps_c[(1 * 8 + s) * 2 + 0], F1, yy);
+              yy = map2(a.maps_c[(1 * 8 + s) * 2 + 1], B1, yy);
               y[8 * h + s] = yy;
             }
           }
@@ -580,28 +635,51 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         for (int i = 0; i < 16; ++i) y[i] = make_float2(0.f, 0.f);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&misc->uempty[st]);     // this warp no longer reads the handoff buffers
+      tr_mark(a, it, 8, p == trp);
+      hb_arrive(HB_UEMPTY + st);                            // this warp no longer reads the handoff buffers
       // first symbol of the next thread (across warps through shared memory)
       if (lane == 0) misc->yex[warp] = y[0];
       y[16] = make_float2(__shfl_down_sync(0xffffffffu, y[0].x, 1), __shfl_down_sync(0xffffffffu, y[0].y, 1));
       bar_post();
+      tr_mark(a, it, 9, p == trp);
       if (lane == 31 && warp + 1 < POST_WARPS) y[16] = misc->yex[warp + 1];
 
       // ---- differential decisions: symbols 16p .. 16p + 15 against their successors ------------------------------------
       {
         const int e0 = p * 16;
         const int nd = pl.d1 - pl.d0;                   // multiple of 32, <= TILE_SYMS
+        // d = y[k+1] conj(y[k]) rho in accumulator units (|y| < 2^35, so the products stay far below the fp32 range).
+        // DQPSK: the dibit of psk_decide() is (sign(dr + di), sign(dr - di)) whenever neither sum is exactly zero -- two funnel
+        // shifts, no branches, the 16 symbols independent of each other; an exact zero anywhere sends the thread through the
+        // literal decision once more.
         uint32_t part = 0;
+        if (a.bps == 2) {
+          float zmin = 1.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 prev = y[i], cur = y[i + 1];
-          // the products reach 2^60 in accumulator units: scale one factor down (a positive factor does not move the angle)
-          const float cx = cur.x * 5.9604645e-8f, cy = cur.y * 5.9604645e-8f;
-          const float tr = fmaf(cx, prev.x, cy * prev.y), ti = fmaf(cy, prev.x, -cx * prev.y);
-          if (a.bps == 2) {
+          for (int i = 0; i < 16; ++i) {
+            const float2 prev = y[i], cur = y[i + 1];
+            const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
             const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
-            part = (part << 2) | psk_decide<float>(dr, di, 2);
-          } else {
+            const float sa = dr + di, sb = dr - di;
+            part = __funnelshift_l(__float_as_uint(sa), part, 1);
+            part = __funnelshift_l(__float_as_uint(sb), part, 1);
+            zmin = fminf(zmin, fminf(fabsf(sa), fabsf(sb)));
+          }
+          if (!(zmin > 0.f) && e0 < nd && e0 < TILE_SYMS) {   // exact zero: literal evaluation (only threads whose word is stored)
+            part = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {       // (unrolled: a dynamic index would put y[] into local memory)
+              const float2 prev = y[i], cur = y[i + 1];
+              const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
+              const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
+              part = (part << 2) | psk_decide<float>(dr, di, 2);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 prev = y[i], cur = y[i + 1];
+            const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
             const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y);
             part = (part << 1) | (dr < 0.f ? 1u : 0u);
           }
@@ -614,7 +692,7 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         }
         if (p == 0 && !okv) a.redo_list[atomicAdd(a.redo_count, 1u)] = t;
       }
-      tr_mark(a, it, 5, p == 0);
+      tr_mark(a, it, 5, p == trp);
       bar_post();                                        // tot / yex / carry are rewritten by the next tile
     }
   }
@@ -826,8 +904,35 @@ extern "C" int fb_debug_mma_trace(fb_handle* h, long long* out, int n_ctas) {
 
 // Launches the tensor-core kernel over `n_tiles` tile descriptors (tile size TILE_SYMS).  redo: device buffer of
 // 1 + n_tiles uint32 (count, then the tiles the fp32 kernel must evaluate); the count is zeroed here.
-int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, const void* d_samples, int dtype, const PskTile* d_tiles,
-                      uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo) {
+// 2-D tensor map over the float32 sample buffer: row r = elements [80 r, 80 r + 164) (rows overlap: the stride is one segment),
+// box = 84 x QBOX elements, so that a box lands as QBOX segments at the 336-byte pitch of the staged layout.  Returns the row count.
+typedef CUresult (*fb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static uint32_t make_sample_tmap(const void* d_samples, uint64_t total_samples, CUtensorMap* tm) {
+  using S = Sched10;
+  static fb_tmap_encode_fn enc = nullptr;
+  static bool tried = false;
+  memset(tm, 0, sizeof(*tm));
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (fb_tmap_encode_fn)fn;
+    else cudaGetLastError();
+  }
+  const uint64_t inner = (uint64_t)S::SEG + S::SEGB / 4;          // 164: a box (84 wide) may start anywhere inside its first segment
+  if (!enc || getenv("FB_PSK_NO_TMA") || ((uintptr_t)d_samples & 15) || total_samples < inner + (uint64_t)S::SEG * SEGS) return 0;
+  const uint64_t rows = (total_samples - inner) / S::SEG + 1;
+  if (rows > 0xffffffffull) return 0;
+  const cuuint64_t gdim[2] = {inner, rows}, gstr[1] = {(cuuint64_t)S::SEG * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)(S::SEGB / 4), (cuuint32_t)QBOX}, estr[2] = {1, 1};
+  if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(d_samples), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+  return (uint32_t)rows;
+}
+
+int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, const void* d_samples, uint64_t total_samples, int dtype,
+                      const PskTile* d_tiles, uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo) {
   int rc;
   MmaTables* T = get_tables(h, d, taps, &rc);
   if (!T || !T->usable) return rc ? rc : FB_EUNSUPPORTED;
@@ -841,8 +946,11 @@ int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, c
     for (int s = 0; s < 7; ++s) a.lam_pow[i][s] = T->lam_pow[i][s];
     a.slow_p[2 * i] = d.slow_p[2 * i]; a.slow_p[2 * i + 1] = d.slow_p[2 * i + 1];
   }
+  for (int i = 0; i < 32; ++i) a.maps_c[i] = make_float4(T->maps[i].x, T->maps[i].z, T->maps[i].y, T->maps[i].w);
   a.state_scale = T->state_scale;
   a.rho = make_float2(d.rho[0], d.rho[1]);
+  CUtensorMap tm;
+  a.tm_rows = dtype == FB_F32 ? make_sample_tmap(d_samples, total_samples, &tm) : (memset(&tm, 0, sizeof(tm)), 0u);
   a.bits = d_bits; a.redo_count = d_redo; a.chunk_ctr = d_redo + 1; a.redo_list = d_redo + 2;
   if (const char* e = getenv("FB_MMA_DBG")) a.dbg = atoi(e);
   if (getenv("FB_MMA_TRACE")) {
@@ -857,7 +965,7 @@ int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, c
 #define FB_MMA_LAUNCH(TIN)                                                                                              \
   do {                                                                                                                  \
     FB_CUDA(h, cudaFuncSetAttribute(psk_mma_kernel<TIN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-    psk_mma_kernel<TIN, S><<<grid, ALL_THREADS, smem, h->stream>>>(a);                                   \
+    psk_mma_kernel<TIN, S><<<grid, ALL_THREADS, smem, h->stream>>>(a, tm);                                 \
   } while (0)
   if (dtype == FB_F32) FB_MMA_LAUNCH(float);
   else if (dtype == FB_F64) FB_MMA_LAUNCH(double);

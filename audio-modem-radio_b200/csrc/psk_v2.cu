@@ -843,7 +843,7 @@ static void make_job(const fb_psk_design& d, int rec, int64_t N, int k_lo, int k
 
 template <typename TIn>
 static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthreads, size_t smem, const PskEdgeArgs& ea,
-                      bool use_mma, const fb_psk_design& d, const float* taps, int dtype) {
+                      bool use_mma, const fb_psk_design& d, const float* taps, int dtype, uint64_t total_samples) {
   // edge windows on the second stream, interior tiles on the first: they write disjoint words
   FB_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   FB_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -860,7 +860,7 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
     // interior tiles on the tensor pipe (psk_mma.cu); the few tiles it hands back (samples outside the fp16 split's range)
     // are then evaluated by the fp32 kernel below, CTAs striding over the redo list
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
-    int rc = fb_psk_mma_launch(h, d, taps, ma.samples, dtype, ma.tiles, n_tiles, ma.bits, (uint32_t*)h->redo.p);
+    int rc = fb_psk_mma_launch(h, d, taps, ma.samples, total_samples, dtype, ma.tiles, n_tiles, ma.bits, (uint32_t*)h->redo.p);
     if (rc) return rc;
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     ma.redo = (const uint32_t*)h->redo.p;
@@ -1164,9 +1164,9 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   ea.scratch = (double*)h->scratch.p; ea.bits = (uint32_t*)h->bits.p; ea.n_jobs = (int)jobs.size(); ea.d = d;
 
   const bool mma_now = use_mma && !emulate_only && T == fb_psk_mma_tile_syms();
-  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
-  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
-  else rc = launch_psk<int16_t>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype);
+  if (dtype == FB_F32) rc = launch_psk<float>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype, total_samples);
+  else if (dtype == FB_F64) rc = launch_psk<double>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype, total_samples);
+  else rc = launch_psk<int16_t>(h, ma, n_tiles, nthreads, smem, ea, mma_now, d, taps, dtype, total_samples);
   if (rc) return rc;
 
   rc = fb_bits_backend(h, n_rec, (const RecPlan*)h->plans.p, plans, bps, (const uint32_t*)h->bits.p, d_out, d_out_len, d_sync, d_status);

@@ -34,7 +34,9 @@ def period(i):
     return np.median(t[:, 1:, i] - t[:, :-1, i])
 print(f"MMA warps : wait full {med(0, 1):7.0f} | MMA phase (incl. wait for the handoff buffer) {med(1, 2):7.0f} | period {period(0):7.0f} clk")
 print(f"post warps: wait ufull {med(3, 4):7.0f} | scan + symbols + slicer {med(4, 5):7.0f} | period {period(3):7.0f} clk")
-print(f"loaders   : loads issued -> stage free {med(10, 11):7.0f} | convert + store {med(11, 12):7.0f} | period {period(10):7.0f} clk")
+print(f"MMA detail: full -> handoff buffer free {med(1, 14):7.0f} | first m-tile {med(14, 15):7.0f} | second m-tile + arrive {med(15, 2):7.0f}")
+print(f"post detail: tile/non-chained + features + warp scan {med(4, 6):7.0f} | barrier {med(6, 7):7.0f} | carries + symbols {med(7, 8):7.0f} | yex barrier {med(8, 9):7.0f} | slicer + store {med(9, 5):7.0f}")
+print(f"loaders   : wait for the first box {med(10, 11):7.0f} | convert + store (incl. waits for the other boxes) {med(11, 12):7.0f} | period {period(10):7.0f} clk")
 
 per = t[:, 1:, 0] - t[:, :-1, 0]
 print(f"MMA period: mean {per.mean():.0f} p90 {np.percentile(per, 90):.0f} max {per.max():.0f}; first stamp spread across CTAs {(buf[:, 0, 0].max() - buf[:, 0, 0].min())} clk (different SM clocks: indicative only)")
@@ -43,3 +45,14 @@ print(f"47 tiles took: median {np.median(tot):.0f} min {tot.min()} max {tot.max(
 
 ns = buf[:, 47, 13] - buf[:, 0, 13]
 print(f"47 tiles took (globaltimer): median {np.median(ns):.0f} ns -> SM clock {np.median(tot) / np.median(ns) * 1000:.0f} MHz; CTA start spread {(buf[:, 0, 13].max() - buf[:, 0, 13].min()) / 1e3:.1f} us; first tile .. tile 47 end spread {(buf[:, 47, 13].max() - buf[:, 0, 13].min()) / 1e3:.1f} us")
+
+if os.environ.get("FB_TRACE_DUMP"):
+    cta = int(os.environ["FB_TRACE_DUMP"])
+    base = buf[cta, 8, 0]
+    names = {0: "M.top", 1: "M.full", 13: "M.rangechk", 14: "M.uempty", 15: "M.mt0", 2: "M.done", 3: "P.top", 4: "P.ufull", 6: "P.scan", 7: "P.bar", 8: "P.sym", 9: "P.yex", 5: "P.done", 10: "L.top", 11: "L.issued", 12: "L.conv"}
+    ev = []
+    for it in range(8, 14):
+        for slot, nm in names.items():
+            ev.append((int(buf[cta, it, slot] - base), f"{nm}[{it}]"))
+    for tm, nm in sorted(ev):
+        print(f"{tm:8d} {nm}")
