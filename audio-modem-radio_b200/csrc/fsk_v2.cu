@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(FB_THREADS) fsk_vote_kernel(const uint8_t* cmp
 // ------------------------------------------------------------------------------------------------ host side
 struct FskPlans {
   std::map<int64_t, std::pair<cufftHandle, cufftHandle>> plans;   // N -> (D2Z, Z2D)
+  std::map<int64_t, uint64_t> used;                                // N -> tick of the last use (LRU eviction)
+  uint64_t tick = 0;
 };
+constexpr size_t FSK_PLAN_CACHE = 16;
 static std::map<fb_handle*, FskPlans> g_fsk_plans;
 
 void fb_fsk_release(fb_handle* h) {
@@ -218,9 +221,14 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
         const int64_t N = (int64_t)p.n;
         auto it = fp.plans.find(N);
         if (it == fp.plans.end()) {
-          if (fp.plans.size() >= 8) {                          // bounded plan cache
-            for (auto& q : fp.plans) { cufftDestroy(q.second.first); cufftDestroy(q.second.second); }
-            fp.plans.clear();
+          if (fp.plans.size() >= FSK_PLAN_CACHE) {             // bounded plan cache: evict the least recently used length
+            auto lru = fp.used.begin();
+            for (auto u = fp.used.begin(); u != fp.used.end(); ++u) if (u->second < lru->second) lru = u;
+            auto victim = fp.plans.find(lru->first);
+            FB_CUDA(h, cudaStreamSynchronize(h->stream));      // transforms queued on the victim's plans must have finished
+            cufftDestroy(victim->second.first); cufftDestroy(victim->second.second);
+            fp.plans.erase(victim);
+            fp.used.erase(lru);
           }
           cufftHandle a, b;
           if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2D, 1) != CUFFT_SUCCESS) {
@@ -230,6 +238,7 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
           cufftSetStream(a, h->stream); cufftSetStream(b, h->stream);
           it = fp.plans.emplace(N, std::make_pair(a, b)).first;
         }
+        fp.used[N] = ++fp.tick;
         uint32_t* d_words = (uint32_t*)h->bits.p + p.word_off;
         rc = fsk_one(h, d, N, p.ndsym, d_words, it->second.first, it->second.second, fbuf[0] + f_off[r], fbuf[1] + f_off[r],
                      (cufftDoubleComplex*)sc, (cufftDoubleComplex*)(sc + o_Z), (double*)(sc + o_env), (uint8_t*)(sc + o_cmp));

@@ -250,12 +250,19 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
     // ================================================== loader warps ==================================================
     // A tile's samples arrive by TMA (requested by the first thread of the post warps, see there), four boxes, each
     // completing its own mbarrier.  120 converter threads rewrite the landed slots in place, [8 x fp32] -> [8 x fp16 hi |
-    // 8 x fp16 lo] (x 2^14; 22 significant bits): thread lt = 10 rg + c owns slot c of segments rg, rg + 12, ...  Tiles at the
+    // 8 x fp16 lo] (x 2^14; 22 significant bits): a thread owns slot c of segments rg, rg + 12, ... (mapping below)  Tiles at the
     // ends of a recording and other sample types come through guarded loads instead.
     const int lt = (int)threadIdx.x;
     constexpr int UPS = S::SEG / 8, LROWS = 12, NIT = (SEGS + LROWS - 1) / LROWS;
     const bool lactive = lt < UPS * LROWS;
-    const int rg = lt / UPS, c = lt - rg * UPS;
+    // Slot of this thread inside a row group of 12 segments.  A slot is 32 bytes read and written as two 16-byte halves, so
+    // the 8 lanes of a quarter warp must hit 8 different 16-byte bank groups: bank group = (21 seg + 2 c) mod 8, i.e. four
+    // slots of an even segment give {0,2,4,6} + const and four of an odd one the other parity.  Threads 0..95: segment pairs
+    // x slot blocks c 0-3 / 4-7; threads 96..119: the slots c 8, 9 of segments {0,1,4,5}, {2,3,6,7}, {8,9,10,11} (the last
+    // group keeps a 2-way conflict).  (The plain mapping 10 rg + c made every one of these accesses a 2-way conflict.)
+    int rg, c;
+    if (lt < 96) { const int w16 = lt & 15, l8 = w16 & 7; rg = 2 * (lt >> 4) + (l8 >> 2); c = 4 * (w16 >> 3) + (l8 & 3); }
+    else { const int j = lt - 96, g3 = j >> 3, l8 = j & 7, k = l8 >> 1; rg = g3 == 2 ? 8 + k : 2 * g3 + (k & 1) + 4 * (k >> 1); c = 8 + (l8 & 1); }
     for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
       const uint32_t par = (it >> 1) & 1;
@@ -298,7 +305,7 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         const int64_t c_w0a = w0 - (int64_t)((pl.off + (uint64_t)w0) & 7);
         for (int item = 0; item < NIT && lactive; ++item) {       // tiles at the ends of a recording, and other sample types: guarded loads
           if (rg + LROWS * item >= SEGS) break;
-          const int64_t n = c_w0a + (int64_t)lt * 8 + (int64_t)item * (LROWS * S::SEG);
+          const int64_t n = c_w0a + (int64_t)(rg * S::SEG + c * 8) + (int64_t)item * (LROWS * S::SEG);
           float v[8];
           if (n >= 0 && n + 8 <= c_N) {
             Raw8<TIn> r;

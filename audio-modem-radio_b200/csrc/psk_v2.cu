@@ -915,7 +915,9 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   // ---- host samples, large batch: pipeline the host->device copy with the kernels --------------------------------------
   // The batch is cut into up to 16 groups of whole recordings; group g+1 is copied on the copy stream while group g is
   // demodulated (device-resident recursion on the work stream), so only the first group's copy is exposed.
-  if (!(flags & FB_SAMPLES_ON_DEVICE) && n_rec >= 8 && (size_t)offsets[n_rec] * esz >= ((size_t)256 << 20)) {
+  size_t pipe_min_bytes = (size_t)256 << 20;
+  if (const char* e = getenv("FB_PSK_PIPE_MB")) pipe_min_bytes = (size_t)std::max(0, atoi(e)) << 20;   // tests: force the pipelined path on small batches
+  if (!(flags & FB_SAMPLES_ON_DEVICE) && n_rec >= 8 && (size_t)offsets[n_rec] * esz >= pipe_min_bytes) {
     const uint64_t total = offsets[n_rec], total_out_b = out_offsets[n_rec];
     int rc;
     if ((rc = fb_ensure(h, h->in, (size_t)total * esz + 16))) return rc;
@@ -999,7 +1001,15 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   std::vector<EdgeJob> jobs;
   uint64_t words = 0, scratch_doubles = 0;
   uint32_t n_tiles = 0;
-  const uint64_t EMU_MAX = 1ull << 22;     // samples a single window may span when the whole record is emulated
+  // Whole-record float64 evaluation (`emulate_only` parameter sets, e.g. PSK31's 62 Hz band): one window per recording,
+  // 3 doubles of scratch per sample.  Bounded by half of the free device memory (2^26 samples at most) instead of a fixed
+  // 4 M samples, so that a 3-minute recording of such a set returns the reference's bytes as well.
+  const uint64_t EMU_MAX = 1ull << 26;
+  uint64_t emu_budget = 0;
+  {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) emu_budget = (uint64_t)fr / 2 / 8; else cudaGetLastError();
+  }
   for (int r = 0; r < n_rec; ++r) {
     RecPlan& p = plans[r];
     p.off = offsets[r];
@@ -1030,7 +1040,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
       }
     }
     if (whole) {
-      if (p.n > EMU_MAX) { p.status = FB_ST_UNSUPPORTED; p.ndsym = 0; continue; }
+      if (p.n > EMU_MAX || scratch_doubles + 3 * p.n + 4096 > emu_budget + h->scratch.cap / 8) { p.status = FB_ST_UNSUPPORTED; p.ndsym = 0; continue; }
       make_job(d, r, N, 0, p.nsym - 1, scratch_doubles, jobs);
     }
   }

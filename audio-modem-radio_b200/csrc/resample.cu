@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(FB_THREADS) resample_bins_kernel(const cufftDo
   }
 }
 
-struct ResamplePlans { std::map<std::pair<int64_t, int>, cufftHandle> plans; };   // (length, 0 = D2Z | 1 = Z2D)
+struct ResamplePlans {                                   // (length, 0 = D2Z | 1 = Z2D) -> plan, with the tick of its last use
+  std::map<std::pair<int64_t, int>, cufftHandle> plans;
+  std::map<std::pair<int64_t, int>, uint64_t> used;
+  uint64_t tick = 0;
+};
 static std::map<fb_handle*, ResamplePlans> g_rs_plans;
 
 void fb_resample_release(fb_handle* h) {
@@ -50,15 +54,20 @@ static int rs_plan(fb_handle* h, int64_t len, int inverse, cufftHandle* out) {
   auto key = std::make_pair(len, inverse);
   auto it = rp.plans.find(key);
   if (it == rp.plans.end()) {
-    if (rp.plans.size() >= 8) {
-      for (auto& p : rp.plans) cufftDestroy(p.second);
-      rp.plans.clear();
+    if (rp.plans.size() >= 16) {                           // evict the least recently used plan
+      auto lru = rp.used.begin();
+      for (auto u = rp.used.begin(); u != rp.used.end(); ++u) if (u->second < lru->second) lru = u;
+      FB_CUDA(h, cudaStreamSynchronize(h->stream));        // transforms queued on it must have finished
+      cufftDestroy(rp.plans[lru->first]);
+      rp.plans.erase(lru->first);
+      rp.used.erase(lru);
     }
     cufftHandle pl;
     if (cufftPlan1d(&pl, (int)len, inverse ? CUFFT_Z2D : CUFFT_D2Z, 1) != CUFFT_SUCCESS) { h->err = "cufftPlan1d failed"; return FB_ECUDA; }
     cufftSetStream(pl, h->stream);
     it = rp.plans.emplace(key, pl).first;
   }
+  rp.used[key] = ++rp.tick;
   *out = it->second;
   return FB_OK;
 }

@@ -139,10 +139,27 @@ class Engine:
         sizes = (sizes + np.uint64(3)) // np.uint64(4) * np.uint64(4)
         return np.concatenate([[np.uint64(0)], np.cumsum(sizes, dtype=np.uint64)]).astype(np.uint64)
 
-    def psk_demod_batch(self, recordings: Sequence[np.ndarray], d: PskDesign) -> List[DemodResult]:
-        """Host-buffer batch call: recordings (same dtype: float32, float64 or int16 PCM) -> DemodResult each."""
+    def psk_demod_batch(self, recordings: Sequence[np.ndarray], d: PskDesign, exact_silence: bool = True) -> List[DemodResult]:
+        """Host-buffer batch call: recordings (same dtype: float32, float64 or int16 PCM) -> DemodResult each.
+
+        exact_silence: recordings that contain a long run of EXACT zeros (zero-padded WAVs without a noise floor) are
+        demodulated by the float64 step-by-step evaluation of the reference's recurrences (the design's `emulate_only`
+        path): inside such a run the reference's decisions (modem.py:216-241) ride on the decaying leakage of its IIR
+        state, far below what the factorised float32 path resolves."""
         if len(recordings) == 0:
             return []
+        if exact_silence and not d.emulate_only:
+            min_run = max(64, int(d.w_bp) // 5)            # leakage still >= 1e-2 of the signal next to it: float32 is exact enough
+            silent = [i for i, r in enumerate(recordings) if len(r) <= EMULATE_MAX_SAMPLES and has_zero_run(r, min_run)]
+            if silent:
+                de = emulating_copy(d)
+                res: List[Optional[DemodResult]] = [None] * len(recordings)
+                for i, v in zip(silent, self.psk_demod_batch([recordings[i] for i in silent], de, exact_silence=False)):
+                    res[i] = v
+                rest = [i for i in range(len(recordings)) if res[i] is None]
+                for i, v in zip(rest, self.psk_demod_batch([recordings[i] for i in rest], d, exact_silence=False)):
+                    res[i] = v
+                return res      # type: ignore[return-value]
         dt = recordings[0].dtype
         if any(r.dtype != dt for r in recordings):
             raise ValueError("all recordings of one batch must share a dtype")
@@ -173,6 +190,31 @@ class Engine:
         _lib.check(self.lib, self.handle,
                    self.lib.fb_psk_last_bits(self.handle, rec, buf.ctypes.data, len(buf), ctypes.byref(nb)), "fb_psk_last_bits")
         return np.unpackbits(buf)[: nb.value]
+
+
+EMULATE_MAX_SAMPLES = 1 << 26            # whole-record float64 evaluation: csrc/psk_v2.cu EMU_MAX
+
+
+def has_zero_run(x: np.ndarray, min_run: int) -> bool:
+    """True when x holds at least `min_run` consecutive samples that are exactly zero."""
+    n = len(x)
+    if n < min_run:
+        return False
+    nz = np.flatnonzero(x)
+    if len(nz) == 0:
+        return True
+    if nz[0] >= min_run or n - 1 - nz[-1] >= min_run:
+        return True
+    return len(nz) > 1 and int(np.diff(nz).max()) - 1 >= min_run
+
+
+def emulating_copy(d: PskDesign) -> PskDesign:
+    """The same parameter set evaluated step by step in float64 on the device (no factorised interior kernel)."""
+    import copy
+    import dataclasses
+    cs = copy.copy(d.c_struct)                             # ctypes structures copy by value
+    cs.emulate_only = 1
+    return dataclasses.replace(d, emulate_only=True, c_struct=cs)
 
 
 _default: Optional[Engine] = None

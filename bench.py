@@ -79,6 +79,70 @@ def synth_batch_device(torch, dev, n_rec: int, n_samples: int, snr_db: float, ra
 
 
 # ----------------------------------------------------------------------------------------- clocks
+def bind_rank_to_gpu_cpus(local: int, world: int):
+    """Binds this rank's threads to its share of the CPUs next to its GPU (NVML affinity mask, else the PCI device's
+    local_cpulist; when every GPU reports the same set the ranks split it) BEFORE any pinned buffer is allocated, so that the
+    staging pages are first-touched on that socket.  Returns a description for the JSON line."""
+    info = {"bound": False}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        bind_rank_to_gpu_cpus.allowed = allowed          # restored before the CPU baseline leg (it uses every host core)
+        cpus, numa = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1]
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            node_path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+            if os.path.exists(node_path):
+                numa = int(open(node_path).read().strip())
+        except Exception:      # noqa: BLE001
+            cpus = None
+        cpus = [c for c in (cpus or allowed) if c in allowed] or allowed
+        share = cpus[local % max(1, world)::max(1, world)] if len(cpus) >= 2 * world else cpus   # every GPU the same set: split it
+        os.sched_setaffinity(0, share)
+        info = {"bound": True, "gpu_cpu_affinity": f"{cpus[0]}-{cpus[-1]} ({len(cpus)} cpus)", "numa_node": numa,
+                "rank_cpus": len(share)}
+    except Exception as e:      # noqa: BLE001
+        info = {"bound": False, "error": str(e)[:120]}
+    return info
+
+
+def h2d_probe(torch, dev, dist, src_pinned, chunk_bytes=1 << 30, reps=8):
+    """Bare pinned-host -> device copy bandwidth with every rank copying at the same time (the host-side roof of `e2e`):
+    `reps` cudaMemcpyAsync of `chunk_bytes` from different places of this rank's pinned staging buffer, CUDA events."""
+    src = src_pinned.view(torch.uint8)
+    chunk_bytes = min(chunk_bytes, src.numel())
+    dst = torch.empty(chunk_bytes, dtype=torch.uint8, device=dev)
+    n_off = max(1, src.numel() // chunk_bytes)
+    dst.copy_(src[:chunk_bytes], non_blocking=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        o = (i % n_off) * chunk_bytes
+        dst.copy_(src[o:o + chunk_bytes], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = reps * chunk_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    agg, lo = gbs, gbs
+    if dist is not None:
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        agg = float(t.item())
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        lo = float(t.item())
+    del dst
+    return {"aggregate_gbs": agg, "min_rank_gbs": lo, "this_rank_gbs": gbs, "chunk_bytes": chunk_bytes, "reps": reps,
+            "what": "concurrent pinned cudaMemcpyAsync H2D on all ranks, no kernels: the host-side roof of e2e"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -268,6 +332,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_rank_to_gpu_cpus(local, world) if args.impl != "reference" else None
     workload = f"qpsk{BAUD}_c{int(CARRIER)}_{args.recordings}x{args.seconds}s_f32"
     config = {"workload": workload, "scheme": "DQPSK (modem.qpsk_demodulate)", "baud": BAUD, "carrier_hz": CARRIER,
               "fs_hz": FS, "recordings_per_gpu": args.recordings, "seconds_per_recording": args.seconds,
@@ -295,7 +360,11 @@ def main():
         cb["value"] = v
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
                           "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": dict(config, reference_sample=(f"each step demodulates {cb['cores']} x 20-s recordings of this workload (one per "
+                                                                   "host core, the same DQPSK parameter set and SNR), NOT the 256 x 180-s batch: throughput "
+                                                                   "is linear in the record length (SURVEY 6), the value is samples / wall time of that sample"),
+                                        frame_parse="not included (the reference arm times the demodulator only; the product arm parses frames too)"),
                           "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
               file=result_out, flush=True)
@@ -452,6 +521,7 @@ def main():
                 rc = eng.lib.fb_parse_frames_batch(eng.handle, n_rec, out_h.data_ptr(), oo_p, ol_h.data_ptr(), MAXF,
                                                    ctypes.addressof(fr_h), nf_h.ctypes.data, pb_h.ctypes.data, 0)
                 _lib.check(eng.lib, eng.handle, rc, "fb_parse_frames_batch")
+            probe = h2d_probe(torch, dev, dist, pcm)
             step_pcm()
             barrier()
             t0 = time.perf_counter()
@@ -466,6 +536,7 @@ def main():
             e2e_pcm16 = {"value": samples_per_step / s_pcm / 1e6, "unit": "Msamples/s", "ms_per_step": s_pcm * 1e3,
                          "h2d_bytes_per_step": int(batch.numel() * 2), "d2h_bytes_per_step": int(out_offsets[-1]) + n_rec * 20,
                          "steps": args.e2e_steps, "payload_bytes_valid": int(pb_h.sum()), "host_format": "PCM16",
+                         "h2d_probe": probe, "h2d_gbs_achieved_all_ranks": batch.numel() * 2 * world / s_pcm / 1e9, "cpu_binding": binding,
                          "api": "fb_psk_demod_batch (FB_S16) + fb_parse_frames_batch with host pointers (fbdsp.Engine)",
                          "note": "host buffers hold the WAV parts' PCM16 payload (what decode_wav_file reads; the device scales by "
                                  "1/32768 exactly like soundfile); e2e_f32 is the same call on float32 host buffers"}
@@ -492,19 +563,27 @@ def main():
     k_ms = float(np.mean([k for k in kernel_ms if k and k > 0])) if kernel_ms else float("nan")
     alg_bytes = n_rec * n_samp * 4 + raw_bytes
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"kernel": "psk_main_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-                "algorithmic_bytes_per_launch": alg_bytes,
+    mma = not os.environ.get("FB_PSK_NO_MMA")
+    prof = "r02_psk_mma_ncu.txt" if mma else "r01_psk_main_ncu.txt"
+    roofline = {"kernel": "psk_mma_kernel<float, Sched10>" if mma else "psk_main_kernel<float>", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "traffic_source": None, "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms / ms_per_step, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "note": "fp32-FMA co-limited, not HBM-bound: 32 (FIR, FFMA2) + 8 (slow-pole features) + ~8 FMA per sample, "
-                        "so >= 6.1 ms at the measured 124 FMA/clk/SM (DESIGN.md 4); traffic = ncu dram bytes of the same "
-                        "kernel per launch, scaled from the 32-recording capture in profiles/"}
-    try:      # dram__bytes_read+write per sample from the committed ncu capture (profiles/r01_psk_main_ncu.txt)
-        for ln in open(os.path.join(ROOT, "profiles", "r01_psk_main_ncu.txt")):
+                "note": ("tensor-pipe kernel (mma.sync HMMA on fp16 hi/lo split operands, TMA-staged samples, DESIGN.md 4.1): bound by "
+                         "shared-memory wavefronts and the latency of its three warp roles, not by HBM; DRAM traffic equals the "
+                         "algorithmic bytes") if mma else
+                        ("fp32-FMA co-limited, not HBM-bound: 32 (FIR, FFMA2) + 8 (slow-pole features) + ~8 FMA per sample, "
+                         "so >= 6.1 ms at the measured 124 FMA/clk/SM (DESIGN.md 4)")}
+    try:      # dram__bytes_read + dram__bytes_write per sample of the same kernel, from the committed `ncu --set full` capture
+        for ln in open(os.path.join(ROOT, "profiles", prof)):
             if ln.startswith("dram_bytes_per_sample"):
                 roofline["traffic"] = float(ln.split()[1]) * n_rec * n_samp
+                roofline["traffic_source"] = (f"static profile: profiles/{prof} (one ncu --set full launch on 32 recordings), bytes per "
+                                              "sample x the samples of this launch; not measured in this run")
     except Exception:      # noqa: BLE001
         pass
+    if getattr(bind_rank_to_gpu_cpus, "allowed", None):
+        os.sched_setaffinity(0, bind_rank_to_gpu_cpus.allowed)
     cb = None if args.no_cpu else cpu_baseline(30)
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -157,3 +157,23 @@ def test_sync_beyond_the_search_head(engine):
         st = o2.qpsk_stages(x, 9600, 9600.0)
         assert r.sync_idx == st["sync"] and r.raw == st["raw"]
     assert res[0].sync_idx > 131072 + 64 and 0 <= res[1].sync_idx < 200 and res[2].sync_idx == -1
+
+
+def test_pipelined_host_copy_equals_single_copy(engine, monkeypatch):
+    """Host batches of >= 256 MB are copied in up to 16 groups on a copy stream while earlier groups are demodulated
+    (csrc/psk_v2.cu); FB_PSK_PIPE_MB lowers the threshold so that a small ragged batch takes that path: the per-recording
+    bytes, sync indices and statuses must equal the single-copy path's."""
+    import fbdsp
+    rng = np.random.default_rng(77)
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    recs = []
+    for i in range(19):
+        _, _, x = sig.kat_signal(sig.qpsk_modulate, 7700 + i, int(rng.integers(200, 1500)), 20, baud=9600, carrier=9600.0)
+        recs.append(np.concatenate([0.01 * rng.standard_normal(int(rng.integers(0, 3000))).astype(np.float32), x]))
+    recs.append(np.zeros(5, np.float32))                        # too short: status, not an exception
+    monkeypatch.delenv("FB_PSK_PIPE_MB", raising=False)
+    want = engine.psk_demod_batch(recs, d, exact_silence=False)
+    monkeypatch.setenv("FB_PSK_PIPE_MB", "0")
+    got = engine.psk_demod_batch(recs, d, exact_silence=False)
+    assert [(r.raw, r.sync_idx, r.status) for r in got] == [(r.raw, r.sync_idx, r.status) for r in want]
+    assert any(len(r.raw) > 100 for r in got)
