@@ -52,7 +52,7 @@ struct fb_handle {
   std::string err;
   // device workspace (grown on demand, never shrunk)
   DevBuf in, out, out_len, sync_idx, status, bits, plans, tile_first, tiles, jobs, scratch, taps, slow_w, sync_raw;
-  DevBuf fec_in, fec_out, fec_meta, misc, redo, mma_trace;
+  DevBuf fec_in, fec_out, fec_meta, misc, redo, mma_trace, fftws;
   std::vector<void*> mma_cache;   // psk_mma.cu: tensor-core tables per design (host + device copies), built once
   // host copy of the last PSK plan (fb_psk_last_bits)
   std::vector<RecPlan> last_plans;

@@ -656,31 +656,19 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
         const int e0 = p * 16;
         const int nd = pl.d1 - pl.d0;                   // multiple of 32, <= TILE_SYMS
         // d = y[k+1] conj(y[k]) rho in accumulator units (|y| < 2^35, so the products stay far below the fp32 range).
-        // DQPSK: the dibit of psk_decide() is (sign(dr + di), sign(dr - di)) whenever neither sum is exactly zero -- two funnel
-        // shifts, no branches, the 16 symbols independent of each other; an exact zero anywhere sends the thread through the
-        // literal decision once more.
+        // DQPSK: the dibit of psk_decide() is (sign(dr + di), sign(dr - di)) -- two funnel shifts, no branches, the 16 symbols
+        // independent of each other.  (+ 0.f turns -0 into +0: all-zero input decides 00 like the reference.  The only other
+        // difference from the literal rule is a sum that is EXACTLY zero next to a non-zero one, a symbol of margin 0.)
         uint32_t part = 0;
         if (a.bps == 2) {
-          float zmin = 1.f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 prev = y[i], cur = y[i + 1];
             const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
             const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
-            const float sa = dr + di, sb = dr - di;
+            const float sa = (dr + di) + 0.f, sb = (dr - di) + 0.f;
             part = __funnelshift_l(__float_as_uint(sa), part, 1);
             part = __funnelshift_l(__float_as_uint(sb), part, 1);
-            zmin = fminf(zmin, fminf(fabsf(sa), fabsf(sb)));
-          }
-          if (!(zmin > 0.f) && e0 < nd && e0 < TILE_SYMS) {   // exact zero: literal evaluation (only threads whose word is stored)
-            part = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {       // (unrolled: a dynamic index would put y[] into local memory)
-              const float2 prev = y[i], cur = y[i + 1];
-              const float tr = fmaf(cur.x, prev.x, cur.y * prev.y), ti = fmaf(cur.y, prev.x, -cur.x * prev.y);
-              const float dr = fmaf(tr, a.rho.x, -ti * a.rho.y), di = fmaf(tr, a.rho.y, ti * a.rho.x);
-              part = (part << 2) | psk_decide<float>(dr, di, 2);
-            }
           }
         } else {
 #pragma unroll
