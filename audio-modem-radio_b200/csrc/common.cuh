@@ -71,8 +71,8 @@ struct fb_handle {
   } while (0)
 
 int fb_ensure(fb_handle* h, DevBuf& b, size_t bytes);
-void fb_fsk_release(fb_handle* h);   // fsk_v2.cu: cuFFT plans cached per handle
-void fb_resample_release(fb_handle* h);   // resample.cu: cuFFT plans cached per handle
+void fb_fsk_release(fb_handle* h);   // fsk_v2.cu
+void fb_resample_release(fb_handle* h);   // resample.cu
 
 // bits back end (backend.cu): first-occurrence magic search + shifted byte packing
 int fb_bits_backend(fb_handle* h, int n_rec, const RecPlan* d_plans, const std::vector<RecPlan>& plans, int bps,
@@ -87,13 +87,14 @@ __device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {  // a*b +
   return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
 }
 // Dibit / bit decision on d = y[k+1] conj(y[k]) rho.  Returns the 2-bit code (b0<<1|b1) for DQPSK
-// (modem.py:219-241: 00 | 01 | 11 | 10 by 90-degree sectors centred on 0, pi/2, pi, -pi/2; d == 0 -> 00)
-// or the single bit for DBPSK (modem.py:105: Re(d) < 0 -> 1).
+// (modem.py:219-241: 00 | 01 | 11 | 10 by 90-degree sectors centred on 0, pi/2, pi, -pi/2) or the single bit for DBPSK
+// (modem.py:105: Re(d) < 0 -> 1).  d == 0: np.angle is atan2(+-0, re): 0 for re = +0 -> 00, +-pi for re = -0 -> 11 (products
+// of symbols below 1e-162 underflow to signed zeros in the reference, too).
 template <typename R>
 __device__ __forceinline__ uint32_t psk_decide(R dr, R di, int bps) {
   const R a = dr + di, b = dr - di;
-  // a > 0: 00 | 01;  else b < 0: 11;  else origin -> 00, otherwise 10   (selects, no branches)
-  const uint32_t q = (a > R(0)) ? ((b > R(0)) ? 0u : 1u) : ((b < R(0)) ? 3u : ((a == R(0) && b == R(0)) ? 0u : 2u));
+  // a > 0: 00 | 01;  else b < 0: 11;  else origin -> 00 / 11 by the sign of the real zero, otherwise 10
+  const uint32_t q = (a > R(0)) ? ((b > R(0)) ? 0u : 1u) : ((b < R(0)) ? 3u : ((a == R(0) && b == R(0)) ? (signbit(dr) ? 3u : 0u) : 2u));
   const uint32_t p = dr < R(0) ? 1u : 0u;
   return bps == 1 ? p : q;
 }

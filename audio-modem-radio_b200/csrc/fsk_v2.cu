@@ -4,17 +4,17 @@
 //   zp_fwd_kernel / zp_bwd_kernel (zp_iir.cuh)   scipy.signal.filtfilt in float64: odd extension by padlen, lfilter_zi
 //                                     start-up, DF2T forward then backward.  Chunk-parallel with coalesced traffic; all
 //                                     recordings of a group in one launch per pass.
-//   cuFFT D2Z -> hilbert_spec -> cuFFT Z2D   scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and one length-N
-//                                     inverse FFT over the whole recording (circular); the library FFT is used for this
-//                                     one library-shaped op exactly as the reference uses pocketfft.  Only the imaginary
-//                                     part needs the inverse (the real part is the input), so it is a real transform.
+//   fb_fft_d2z -> hilbert_spec -> fb_fft_z2d  scipy.signal.hilbert *is* one length-N FFT, a one-sided mask and one length-N
+//                                     inverse FFT over the whole recording (circular): the hand-written float64 FFT of
+//                                     fft.cu (Stockham passes; Bluestein for lengths with other prime factors).  Only the
+//                                     imaginary part needs the inverse (the real part is the input), so it is a real transform.
 // Decision (modem.py:315-323): bits[n] = env_mark[n] > env_space[n]; per bit a majority vote over the centre half
 // (window truncated at the record end; spb < 4 -> empty window -> no bits).  fsk_vote_kernel packs the decided bits
 // into the same big-endian word stream the DPSK kernels write; backend.cu does the magic search and byte packing.
 #include "common.cuh"
 #include "zp_iir.cuh"
 
-#include <cufft.h>
+#include "fft.cuh"
 #include <algorithm>
 #include <map>
 
@@ -23,16 +23,16 @@
 // scipy.signal.hilbert: x_a = ifft(fft(x) h), h = [1, 2, ..., 2, 1 (N even), 0, ...].  Its real part is x itself and its
 // imaginary part is H = irfft(-j X[k]) over 0 < k < N/2 (DC and Nyquist bins dropped): one real-to-complex and one
 // complex-to-real transform instead of a full complex inverse.  In place on the half spectrum.
-__global__ void __launch_bounds__(FB_THREADS) hilbert_spec_kernel(cufftDoubleComplex* X, int64_t N) {
+__global__ void __launch_bounds__(FB_THREADS) hilbert_spec_kernel(double2* X, int64_t N) {
   const int64_t nh = N / 2 + 1;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nh; k += (int64_t)gridDim.x * blockDim.x) {
-    const cufftDoubleComplex v = X[k];
+    const double2 v = X[k];
     const bool keep = k > 0 && 2 * k < N;
-    X[k] = keep ? make_cuDoubleComplex(v.y, -v.x) : make_cuDoubleComplex(0.0, 0.0);      // -j (a + j b) = b - j a
+    X[k] = keep ? make_double2(v.y, -v.x) : make_double2(0.0, 0.0);      // -j (a + j b) = b - j a
   }
 }
 
-// |x_a|^2 N^2 = (N f)^2 + H^2 (cuFFT's inverse is unnormalised).  First tone: keep it; second tone:
+// |x_a|^2 N^2 = (N f)^2 + H^2 (the inverse transform is unnormalised).  First tone: keep it; second tone:
 // cmp[n] = env_mark > env_space  (squares compare like the envelopes; the common N^2 scale drops out)
 __global__ void __launch_bounds__(FB_THREADS) env_kernel(const double* f, const double* H, int64_t N, double* env2, uint8_t* cmp, int second) {
   const double dn = (double)N;
@@ -67,30 +67,18 @@ __global__ void __launch_bounds__(FB_THREADS) fsk_vote_kernel(const uint8_t* cmp
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct FskPlans {
-  std::map<int64_t, std::pair<cufftHandle, cufftHandle>> plans;   // N -> (D2Z, Z2D)
-  std::map<int64_t, uint64_t> used;                                // N -> tick of the last use (LRU eviction)
-  uint64_t tick = 0;
-};
-constexpr size_t FSK_PLAN_CACHE = 16;
-static std::map<fb_handle*, FskPlans> g_fsk_plans;
-
-void fb_fsk_release(fb_handle* h) {
-  auto it = g_fsk_plans.find(h);
-  if (it == g_fsk_plans.end()) return;
-  for (auto& p : it->second.plans) { cufftDestroy(p.second.first); cufftDestroy(p.second.second); }
-  g_fsk_plans.erase(it);
-}
+void fb_fsk_release(fb_handle*) {}   // (nothing cached per handle any more: the FFT workspace is a handle buffer)
 
 // Hilbert envelope compare + vote for one recording whose two tone-filtered copies f0, f1 (float64) are ready
-static int fsk_one(fb_handle* h, const fb_fsk_design& d, int64_t N, int64_t nbits, uint32_t* d_words, cufftHandle p_d2z, cufftHandle p_z2d,
-                   double* f0, double* f1, cufftDoubleComplex* X, cufftDoubleComplex* Z, double* env, uint8_t* cmp) {
+static int fsk_one(fb_handle* h, const fb_fsk_design& d, int64_t N, int64_t nbits, uint32_t* d_words,
+                   double* f0, double* f1, double2* X, double2* Z, double* env, uint8_t* cmp) {
   for (int tone = 0; tone < 2; ++tone) {
     double* ft = tone ? f1 : f0;
-    if (cufftExecD2Z(p_d2z, ft, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
+    int rc = fb_fft_d2z(h, ft, X, N);
+    if (rc) return rc;
     const int g = (int)std::min<int64_t>(148 * 8, (N + FB_THREADS - 1) / FB_THREADS);
     hilbert_spec_kernel<<<g, FB_THREADS, 0, h->stream>>>(X, N);
-    if (cufftExecZ2D(p_z2d, X, reinterpret_cast<double*>(Z)) != CUFFT_SUCCESS) { h->err = "cufftExecZ2D failed"; return FB_ECUDA; }
+    if ((rc = fb_fft_z2d(h, X, reinterpret_cast<double*>(Z), N))) return rc;
     env_kernel<<<g, FB_THREADS, 0, h->stream>>>(ft, reinterpret_cast<const double*>(Z), N, env, cmp, tone);
     h->launches += 2;
   }
@@ -161,7 +149,7 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
   // [ZpRec table].  The two tone filters run for a whole group per launch (grid.y = recording); the Hilbert step then
   // goes recording by recording (one library FFT each).
   const size_t nN = (size_t)maxN + 16;
-  auto al = [](size_t v) { return (v + 255) / 256 * 256; };            // cuFFT wants 16-byte aligned complex buffers
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };            // 16-byte aligned complex buffers
   const size_t o_Z = al((nN / 2 + 2) * 16), o_env = al(o_Z + nN * 16), o_cmp = al(o_env + nN * 8), o_grp = al(o_cmp + nN + 64);
   const int Lc = zp_chunk_len(std::max(d.w[0], d.w[1]));
   std::vector<ZpRec> zr(n_rec);
@@ -192,7 +180,6 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
     if ((rc = fb_ensure(h, h->scratch, o_t + (size_t)n_rec * sizeof(ZpRec) + 64))) return rc;
   }
   char* sc = (char*)h->scratch.p;
-  FskPlans& fp = g_fsk_plans[h];
   if (maxN > 0) {
     ZpRec* d_zr = (ZpRec*)(sc + o_t);
     FB_CUDA(h, cudaMemcpyAsync(d_zr, zr.data(), (size_t)n_rec * sizeof(ZpRec), cudaMemcpyHostToDevice, h->stream));
@@ -219,29 +206,9 @@ extern "C" int fb_fsk_demod_batch(fb_handle* h, const fb_fsk_design* dp, int n_r
         const RecPlan& p = plans[r];
         if (p.status != FB_ST_OK) continue;
         const int64_t N = (int64_t)p.n;
-        auto it = fp.plans.find(N);
-        if (it == fp.plans.end()) {
-          if (fp.plans.size() >= FSK_PLAN_CACHE) {             // bounded plan cache: evict the least recently used length
-            auto lru = fp.used.begin();
-            for (auto u = fp.used.begin(); u != fp.used.end(); ++u) if (u->second < lru->second) lru = u;
-            auto victim = fp.plans.find(lru->first);
-            FB_CUDA(h, cudaStreamSynchronize(h->stream));      // transforms queued on the victim's plans must have finished
-            cufftDestroy(victim->second.first); cufftDestroy(victim->second.second);
-            fp.plans.erase(victim);
-            fp.used.erase(lru);
-          }
-          cufftHandle a, b;
-          if (cufftPlan1d(&a, (int)N, CUFFT_D2Z, 1) != CUFFT_SUCCESS || cufftPlan1d(&b, (int)N, CUFFT_Z2D, 1) != CUFFT_SUCCESS) {
-            h->err = "cufftPlan1d failed";
-            return FB_ECUDA;
-          }
-          cufftSetStream(a, h->stream); cufftSetStream(b, h->stream);
-          it = fp.plans.emplace(N, std::make_pair(a, b)).first;
-        }
-        fp.used[N] = ++fp.tick;
         uint32_t* d_words = (uint32_t*)h->bits.p + p.word_off;
-        rc = fsk_one(h, d, N, p.ndsym, d_words, it->second.first, it->second.second, fbuf[0] + f_off[r], fbuf[1] + f_off[r],
-                     (cufftDoubleComplex*)sc, (cufftDoubleComplex*)(sc + o_Z), (double*)(sc + o_env), (uint8_t*)(sc + o_cmp));
+        rc = fsk_one(h, d, N, p.ndsym, d_words, fbuf[0] + f_off[r], fbuf[1] + f_off[r],
+                     (double2*)sc, (double2*)(sc + o_Z), (double*)(sc + o_env), (uint8_t*)(sc + o_cmp));
         if (rc) return rc;
       }
     }

@@ -792,8 +792,10 @@ __global__ void __launch_bounds__(32) psk_edge_kernel(const PskEdgeArgs a) {
       const int64_t nk = (int64_t)d.n0 + (int64_t)k * d.sps;
       const double sr = U[2 * (nk - jb.la)], si = U[2 * (nk - jb.la) + 1];
       if (k > jb.k_lo) {
-        // s[k] conj(s[k-1]) -- both already carry the LO phase, as in the reference (modem.py:100, 214)
-        const double dr = sr * pr + si * pi, di = si * pr - sr * pi;
+        // s[k] conj(s[k-1]) -- both already carry the LO phase, as in the reference (modem.py:100, 214).  Evaluated the way
+        // numpy's complex multiply is on every FMA-capable host (one rounded product, then a fused multiply-add; b = conj(s[k-1])
+        // = (pr, -pi)): the rounding only matters where the products are denormal or underflow to signed zeros.
+        const double dr = __fma_rn(sr, pr, __dmul_rn(si, pi)), di = __fma_rn(sr, -pi, __dmul_rn(si, pr));
         word = (word << bps) | psk_decide<double>(dr, di, bps);
         if (++filled == dper) {
           *wout++ = __byte_perm(word, 0, 0x0123);

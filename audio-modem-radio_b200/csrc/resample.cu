@@ -4,13 +4,11 @@
 //
 // scipy.signal.resample for a real record (scipy 1.18, `domain='time'`):  X = rfft(x);  keep the first m2 = m/2 + 1 bins,
 // m = min(num, n);  when m is even and num != n the unpaired bin m/2 is doubled (down-sampling) or halved (up-sampling);
-// x_r = irfft(X / (n / num), num).  Here: cuFFT D2Z (the one library-shaped op, as the reference uses pocketfft) ->
-// resample_bins_kernel (crop / zero-pad, unpaired bin, both scale factors folded into one multiply) -> cuFFT Z2D.
+// x_r = irfft(X / (n / num), num).  Here: the hand-written float64 FFT of fft.cu (Stockham passes for 2-3-5-7-smooth lengths,
+// Bluestein otherwise) -> resample_bins_kernel (crop / zero-pad, unpaired bin, both scale factors folded into one multiply)
+// -> the inverse transform of fft.cu.
 #include "common.cuh"
-
-#include <cufft.h>
-#include <map>
-#include <utility>
+#include "fft.cuh"
 
 // channel 0 of `n` interleaved frames, any supported sample type, to float64 (PCM16 scaled by 1/32768 like soundfile)
 template <typename TIn>
@@ -20,11 +18,11 @@ __global__ void __launch_bounds__(FB_THREADS) ingest_kernel(const void* in, uint
 }
 
 // Y[k] = X[k] * scale for k < m2 (bin m/2 adjusted), 0 above; scale = (num / n) / num: irfft's 1/num and scipy's 1/s_fac
-__global__ void __launch_bounds__(FB_THREADS) resample_bins_kernel(const cufftDoubleComplex* X, cufftDoubleComplex* Y, int64_t n, int64_t num) {
+__global__ void __launch_bounds__(FB_THREADS) resample_bins_kernel(const double2* X, double2* Y, int64_t n, int64_t num) {
   const int64_t m = min(n, num), m2 = m / 2 + 1, ny = num / 2 + 1;
   const double scale = 1.0 / (double)n;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ny; k += (int64_t)gridDim.x * blockDim.x) {
-    cufftDoubleComplex v = make_cuDoubleComplex(0.0, 0.0);
+    double2 v = make_double2(0.0, 0.0);
     if (k < m2) {
       v = X[k];
       double f = scale;
@@ -35,42 +33,7 @@ __global__ void __launch_bounds__(FB_THREADS) resample_bins_kernel(const cufftDo
   }
 }
 
-struct ResamplePlans {                                   // (length, 0 = D2Z | 1 = Z2D) -> plan, with the tick of its last use
-  std::map<std::pair<int64_t, int>, cufftHandle> plans;
-  std::map<std::pair<int64_t, int>, uint64_t> used;
-  uint64_t tick = 0;
-};
-static std::map<fb_handle*, ResamplePlans> g_rs_plans;
-
-void fb_resample_release(fb_handle* h) {
-  auto it = g_rs_plans.find(h);
-  if (it == g_rs_plans.end()) return;
-  for (auto& p : it->second.plans) cufftDestroy(p.second);
-  g_rs_plans.erase(it);
-}
-
-static int rs_plan(fb_handle* h, int64_t len, int inverse, cufftHandle* out) {
-  ResamplePlans& rp = g_rs_plans[h];
-  auto key = std::make_pair(len, inverse);
-  auto it = rp.plans.find(key);
-  if (it == rp.plans.end()) {
-    if (rp.plans.size() >= 16) {                           // evict the least recently used plan
-      auto lru = rp.used.begin();
-      for (auto u = rp.used.begin(); u != rp.used.end(); ++u) if (u->second < lru->second) lru = u;
-      FB_CUDA(h, cudaStreamSynchronize(h->stream));        // transforms queued on it must have finished
-      cufftDestroy(rp.plans[lru->first]);
-      rp.plans.erase(lru->first);
-      rp.used.erase(lru);
-    }
-    cufftHandle pl;
-    if (cufftPlan1d(&pl, (int)len, inverse ? CUFFT_Z2D : CUFFT_D2Z, 1) != CUFFT_SUCCESS) { h->err = "cufftPlan1d failed"; return FB_ECUDA; }
-    cufftSetStream(pl, h->stream);
-    it = rp.plans.emplace(key, pl).first;
-  }
-  rp.used[key] = ++rp.tick;
-  *out = it->second;
-  return FB_OK;
-}
+void fb_resample_release(fb_handle*) {}   // (nothing cached per handle any more: the FFT workspace is a handle buffer)
 
 extern "C" int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frames, int n_channels, int dtype, uint64_t n_out,
                                   double* out, int flags) {
@@ -103,15 +66,13 @@ extern "C" int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frame
   else ingest_kernel<int16_t><<<g, FB_THREADS, 0, h->stream>>>(d_in, (uint64_t)n, n_channels, ingest_dst);
   h->launches++;
   if (num != n) {
-    cufftHandle fwd, inv;
-    if ((rc = rs_plan(h, n, 0, &fwd)) || (rc = rs_plan(h, num, 1, &inv))) return rc;
-    cufftDoubleComplex* X = (cufftDoubleComplex*)(ws + o_X);
-    cufftDoubleComplex* Y = (cufftDoubleComplex*)(ws + o_Y);
-    if (cufftExecD2Z(fwd, x, X) != CUFFT_SUCCESS) { h->err = "cufftExecD2Z failed"; return FB_ECUDA; }
+    double2* X = (double2*)(ws + o_X);
+    double2* Y = (double2*)(ws + o_Y);
+    if ((rc = fb_fft_d2z(h, x, X, n))) return rc;
     const int g2 = (int)std::min<int64_t>(148 * 8, (num / 2 + 1 + FB_THREADS - 1) / FB_THREADS);
     resample_bins_kernel<<<g2, FB_THREADS, 0, h->stream>>>(X, Y, n, num);
     h->launches++;
-    if (cufftExecZ2D(inv, Y, y) != CUFFT_SUCCESS) { h->err = "cufftExecZ2D failed"; return FB_ECUDA; }
+    if ((rc = fb_fft_z2d(h, Y, y, num))) return rc;
   }
   FB_CUDA(h, cudaGetLastError());
   if (host_out) FB_CUDA(h, cudaMemcpyAsync(out, y, (size_t)num * 8, cudaMemcpyDeviceToHost, h->stream));
