@@ -6,11 +6,15 @@ namespace {
 
 using fbfft::butterfly;
 
-template <int R>
+template <int R1, int R2>
 __global__ void __launch_bounds__(FB_THREADS) fft_pass_kernel(const double2* __restrict__ x, double2* __restrict__ y, int64_t n, int64_t s,
                                                               int64_t count, int sign) {
+  constexpr int R = R1 * R2;
+  __shared__ double2 w[R];
+  if (threadIdx.x < R) fbfft::roots(w, R, (int)threadIdx.x, sign);
+  __syncthreads();
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x)
-    butterfly<R>(x, y, n, s, t, sign);
+    butterfly<R1, R2>(x, y, n, s, t, sign, w);
 }
 
 __global__ void __launch_bounds__(FB_THREADS) pack_real_kernel(const double* __restrict__ x, double2* __restrict__ c, int64_t n) {
@@ -32,6 +36,37 @@ __global__ void __launch_bounds__(FB_THREADS) hermitian_kernel(const double2* __
 }
 __global__ void __launch_bounds__(FB_THREADS) take_real_kernel(const double2* __restrict__ c, double* __restrict__ y, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = c[i].x;
+}
+
+// ---- even n: the real transform through a complex one of half the length (z[j] = x[2j] + i x[2j+1]) --------------------------
+__global__ void __launch_bounds__(FB_THREADS) pack_pairs_kernel(const double* __restrict__ x, double2* __restrict__ z, int64_t h) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < h; j += (int64_t)gridDim.x * blockDim.x) z[j] = make_double2(x[2 * j], x[2 * j + 1]);
+}
+__global__ void __launch_bounds__(FB_THREADS) unpack_pairs_kernel(const double2* __restrict__ z, double* __restrict__ y, int64_t h) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < h; j += (int64_t)gridDim.x * blockDim.x) { const double2 v = z[j]; y[2 * j] = v.x; y[2 * j + 1] = v.y; }
+}
+// X[k] = (A + B) / 2 - (i / 2) w (A - B),  A = Z[k mod h], B = conj(Z[(h - k) mod h]), w = exp(-2 pi i k / n),  k = 0 .. h
+__global__ void __launch_bounds__(FB_THREADS) r2c_post_kernel(const double2* __restrict__ Z, double2* __restrict__ X, int64_t h) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= h; k += (int64_t)gridDim.x * blockDim.x) {
+    const double2 A = Z[k == h ? 0 : k], Bc = Z[(k == 0 || k == h) ? 0 : h - k];
+    const double2 B = make_double2(Bc.x, -Bc.y);
+    const double2 sm = fbfft::cadd(A, B), df = fbfft::csub(A, B);
+    const double2 w = k == h ? make_double2(-1.0, 0.0) : fbfft::unit(k, 2 * h, -1);
+    const double2 t = fbfft::cmul(w, df);                            // -(i/2) t = (t.y, -t.x) / 2
+    X[k] = make_double2(0.5 * (sm.x + t.y), 0.5 * (sm.y - t.x));
+  }
+}
+// Z'[k] = (A + B) + i w (A - B),  A = X[k], B = conj(X[h - k]), w = exp(+2 pi i k / n),  k = 0 .. h-1;  IDFT_h(Z')[j] = y[2j] + i y[2j+1]
+// (the imaginary parts of X[0] and X[h] are ignored, as numpy.fft.irfft does)
+__global__ void __launch_bounds__(FB_THREADS) c2r_pre_kernel(const double2* __restrict__ X, double2* __restrict__ Zp, int64_t h) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < h; k += (int64_t)gridDim.x * blockDim.x) {
+    double2 A = X[k], Bc = X[h - k];
+    if (k == 0) { A.y = 0.0; Bc.y = 0.0; }
+    const double2 B = make_double2(Bc.x, -Bc.y);
+    const double2 sm = fbfft::cadd(A, B), df = fbfft::csub(A, B);
+    const double2 t = fbfft::cmul(fbfft::unit(k, 2 * h, +1), df);    // i t = (-t.y, t.x)
+    Zp[k] = make_double2(sm.x - t.y, sm.y + t.x);
+  }
 }
 
 // ---- Bluestein:  X[k] = w(k) * sum_j (x[j] w(j)) conj(w(k - j)),   w(i) = exp(sign pi i i^2 / n) -------------------------
@@ -68,12 +103,10 @@ int c2c_smooth(fb_handle* h, double2* a, double2* b, int64_t n, int sign, const 
     const int64_t count = n / r;
     const int g = grid_for(count);
     switch (r) {
-      case 8: fft_pass_kernel<8><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
-      case 4: fft_pass_kernel<4><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
-      case 2: fft_pass_kernel<2><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
-      case 3: fft_pass_kernel<3><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
-      case 5: fft_pass_kernel<5><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
-      case 7: fft_pass_kernel<7><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break;
+#define FB_FFT_PASS(R1, R2) case R1 * R2: fft_pass_kernel<R1, R2><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break
+      FB_FFT_PASS(4, 4); FB_FFT_PASS(4, 2); FB_FFT_PASS(4, 1); FB_FFT_PASS(2, 1); FB_FFT_PASS(3, 3); FB_FFT_PASS(3, 1); FB_FFT_PASS(5, 5); FB_FFT_PASS(5, 1);
+      FB_FFT_PASS(7, 1);
+#undef FB_FFT_PASS
       default: return FB_EINVAL;
     }
     h->launches++;
@@ -124,13 +157,17 @@ int64_t ws_points(int64_t n) {
 
 int fb_fft_d2z(fb_handle* h, const double* d_x, double2* d_X, int64_t n) {
   if (n < 1) return FB_EINVAL;
-  int rc = fb_ensure(h, h->fftws, (size_t)ws_points(n) * sizeof(double2));
+  const bool half = n % 2 == 0;
+  const int64_t nc = half ? n / 2 : n;
+  int rc = fb_ensure(h, h->fftws, (size_t)ws_points(nc) * sizeof(double2));
   if (rc) return rc;
   double2* ws = (double2*)h->fftws.p;
-  pack_real_kernel<<<grid_for(n), FB_THREADS, 0, h->stream>>>(d_x, ws, n);
+  if (half) pack_pairs_kernel<<<grid_for(nc), FB_THREADS, 0, h->stream>>>(d_x, ws, nc);
+  else pack_real_kernel<<<grid_for(n), FB_THREADS, 0, h->stream>>>(d_x, ws, n);
   double2* res;
-  if ((rc = c2c(h, ws, n, -1, &res))) return rc;
-  copy_c_kernel<<<grid_for(n / 2 + 1), FB_THREADS, 0, h->stream>>>(res, d_X, n / 2 + 1);
+  if ((rc = c2c(h, ws, nc, -1, &res))) return rc;
+  if (half) r2c_post_kernel<<<grid_for(nc + 1), FB_THREADS, 0, h->stream>>>(res, d_X, nc);
+  else copy_c_kernel<<<grid_for(n / 2 + 1), FB_THREADS, 0, h->stream>>>(res, d_X, n / 2 + 1);
   h->launches += 2;
   FB_CUDA(h, cudaGetLastError());
   return FB_OK;
@@ -138,13 +175,17 @@ int fb_fft_d2z(fb_handle* h, const double* d_x, double2* d_X, int64_t n) {
 
 int fb_fft_z2d(fb_handle* h, const double2* d_X, double* d_y, int64_t n) {
   if (n < 1) return FB_EINVAL;
-  int rc = fb_ensure(h, h->fftws, (size_t)ws_points(n) * sizeof(double2));
+  const bool half = n % 2 == 0;
+  const int64_t nc = half ? n / 2 : n;
+  int rc = fb_ensure(h, h->fftws, (size_t)ws_points(nc) * sizeof(double2));
   if (rc) return rc;
   double2* ws = (double2*)h->fftws.p;
-  hermitian_kernel<<<grid_for(n / 2 + 1), FB_THREADS, 0, h->stream>>>(d_X, ws, n);
+  if (half) c2r_pre_kernel<<<grid_for(nc), FB_THREADS, 0, h->stream>>>(d_X, ws, nc);
+  else hermitian_kernel<<<grid_for(n / 2 + 1), FB_THREADS, 0, h->stream>>>(d_X, ws, n);
   double2* res;
-  if ((rc = c2c(h, ws, n, +1, &res))) return rc;
-  take_real_kernel<<<grid_for(n), FB_THREADS, 0, h->stream>>>(res, d_y, n);
+  if ((rc = c2c(h, ws, nc, +1, &res))) return rc;
+  if (half) unpack_pairs_kernel<<<grid_for(nc), FB_THREADS, 0, h->stream>>>(res, d_y, nc);
+  else take_real_kernel<<<grid_for(n), FB_THREADS, 0, h->stream>>>(res, d_y, n);
   h->launches += 2;
   FB_CUDA(h, cudaGetLastError());
   return FB_OK;

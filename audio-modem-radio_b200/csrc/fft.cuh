@@ -8,8 +8,8 @@
 //     integer fractions (no table, no accumulated rotation: relative error ~ log2(N) ulp);
 //   * any other N: Bluestein's chirp-z over a power-of-two length M >= 2N - 1 with the same pass kernels, chirp phases from
 //     n^2 mod 2N in 64-bit integers.
-// Real input / output goes through the complex transform (pack / Hermitian expand kernels): these transforms run once per
-// recording and are HBM-bound; the factor two is not where their time goes.
+// Real input / output of even length goes through a complex transform of HALF the length (z[j] = x[2j] + i x[2j+1] and the
+// usual untangling pass); odd lengths take the full-length complex transform (pack / Hermitian expand kernels).
 #pragma once
 #include "common.cuh"
 
@@ -27,37 +27,75 @@ __host__ __device__ __forceinline__ double2 unit(int64_t num, int64_t den, int s
   return make_double2(c, sign < 0 ? -s : s);
 }
 
-// One butterfly of a radix-R Stockham DIF pass.  n: current transform length, s: stride (product of the radices already
-// applied), m = n / R;  butterfly t = p * s + q, p < m, q < s:
-//   a_k = x[q + s (p + k m)];   y[q + s (R p + j)] = (sum_k a_k W_R^(jk)) * exp(sign 2 pi i p j / n)
-template <int R>
-__host__ __device__ __forceinline__ void butterfly(const double2* __restrict__ x, double2* __restrict__ y, int64_t n, int64_t s, int64_t t, int sign) {
-  const int64_t m = n / R, p = t / s, q = t - p * s;
-  double2 a[R], b[R];
-#pragma unroll
-  for (int k = 0; k < R; ++k) a[k] = x[q + s * (p + k * m)];
-  if (R == 2) {
-    b[0] = cadd(a[0], a[1]); b[1] = csub(a[0], a[1]);
-  } else if (R == 4) {
-    const double2 e0 = cadd(a[0], a[2]), e1 = csub(a[0], a[2]), o0 = cadd(a[1], a[3]), o1 = csub(a[1], a[3]);
+// In-place DFT of P points held in registers, v[i] -> sum_i v[i] W_P^(ik);  w: roots table of a multiple R of P (W_R^e),
+// ws = R / P.  P = 2 and 4 need no multiplications.
+template <int P>
+__host__ __device__ __forceinline__ void dft_small(double2 (&v)[P], const double2* __restrict__ w, int ws, int sign) {
+  if (P == 1) return;
+  if (P == 2) {
+    const double2 t = csub(v[0], v[1]);
+    v[0] = cadd(v[0], v[1]); v[1] = t;
+  } else if (P == 4) {
+    const double2 e0 = cadd(v[0], v[2]), e1 = csub(v[0], v[2]), o0 = cadd(v[1], v[3]), o1 = csub(v[1], v[3]);
     const double2 jo1 = sign < 0 ? make_double2(o1.y, -o1.x) : make_double2(-o1.y, o1.x);      // (sign i) * o1
-    b[0] = cadd(e0, o0); b[2] = csub(e0, o0); b[1] = cadd(e1, jo1); b[3] = csub(e1, jo1);
+    v[0] = cadd(e0, o0); v[2] = csub(e0, o0); v[1] = cadd(e1, jo1); v[3] = csub(e1, jo1);
   } else {
-    double2 w[R];                                        // W_R^k = exp(sign 2 pi i k / R)
+    double2 o[P];
 #pragma unroll
-    for (int k = 0; k < R; ++k) w[k] = unit(k, R, sign);
+    for (int j = 0; j < P; ++j) {
+      double2 acc = v[0];
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      double2 acc = a[0];
+      for (int k = 1; k < P; ++k) {
+        const int e = (j * k) % P;
+        if (e == 0) acc = cadd(acc, v[k]); else acc = cadd(acc, cmul(v[k], w[e * ws]));
+      }
+      o[j] = acc;
+    }
 #pragma unroll
-      for (int k = 1; k < R; ++k) acc = cadd(acc, cmul(a[k], w[(j * k) % R]));
-      b[j] = acc;
+    for (int j = 0; j < P; ++j) v[j] = o[j];
+  }
+}
+
+// One butterfly of a radix-R Stockham DIF pass, R = R1 * R2.  n: current transform length, s: stride (product of the radices
+// already applied), m = n / R;  butterfly t = p * s + q, p < m, q < s:
+//   a_i = x[q + s (p + i m)];   y[q + s (R p + k)] = (sum_i a_i W_R^(ik)) * exp(sign 2 pi i p k / n)
+// The R-point DFT is done in registers as R2 DFTs of R1 points, the twiddles W_R^(k1 i2), and R1 DFTs of R2 points
+// (i = i1 R2 + i2, k = k1 + R1 k2).  w: the R roots W_R^e (shared memory on the device: every lane reads the same entry).
+template <int R1, int R2>
+__host__ __device__ __forceinline__ void butterfly(const double2* __restrict__ x, double2* __restrict__ y, int64_t n, int64_t s, int64_t t, int sign,
+                                                   const double2* __restrict__ w) {
+  constexpr int R = R1 * R2;
+  const int64_t m = n / R, p = t / s, q = t - p * s;
+  double2 a[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[i] = x[q + s * (p + i * m)];
+#pragma unroll
+  for (int i2 = 0; i2 < R2; ++i2) {
+    double2 v[R1];
+#pragma unroll
+    for (int i1 = 0; i1 < R1; ++i1) v[i1] = a[i1 * R2 + i2];
+    dft_small<R1>(v, w, R2, sign);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) a[k1 * R2 + i2] = (k1 * i2) % R == 0 ? v[k1] : cmul(v[k1], w[(k1 * i2) % R]);
+  }
+  double2* yo = y + q + s * (R * p);
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) {
+    double2 v[R2];
+#pragma unroll
+    for (int i2 = 0; i2 < R2; ++i2) v[i2] = a[k1 * R2 + i2];
+    dft_small<R2>(v, w, R1, sign);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = k1 + R1 * k2;
+      yo[k * s] = k == 0 ? v[k2] : cmul(v[k2], unit(p * k, n, sign));
     }
   }
-  y[q + s * (R * p)] = b[0];
-#pragma unroll
-  for (int j = 1; j < R; ++j) y[q + s * (R * p + j)] = cmul(b[j], unit(p * j, n, sign));
 }
+
+// the R-th roots of unity a pass needs (R <= FFT_MAX_RADIX)
+constexpr int FFT_MAX_RADIX = 25;
+__host__ __device__ __forceinline__ void roots(double2* w, int R, int k, int sign) { w[k] = unit(k, R, sign); }
 
 // Bluestein chirp w(i) = exp(sign * pi * i * i^2 / n), the phase from i^2 mod 2n in exact integers (i < 2^31)
 __host__ __device__ __forceinline__ double2 chirp(int64_t i, int64_t n, int sign) {
@@ -67,16 +105,24 @@ __host__ __device__ __forceinline__ double2 chirp(int64_t i, int64_t n, int sign
   return make_double2(c, sign < 0 ? -s : s);
 }
 
-// radices of a {2,3,5,7}-smooth length (8s and 4s first: fewer passes); empty when n has another prime factor
+// radices of a {2,3,5,7}-smooth length (composite radices 16 / 9 / 25 first: a pass is one read and one write of all the
+// points, so fewer passes; the radix-R butterfly is a direct R x R product); empty when n has another prime factor
 inline std::vector<int> smooth_radices(int64_t n) {
   std::vector<int> r;
   if (n < 1) return r;
-  int twos = 0;
+  int twos = 0, threes = 0, fives = 0;
   while (n % 2 == 0) { n /= 2; ++twos; }
-  while (twos >= 3) { r.push_back(8); twos -= 3; }
+  while (n % 3 == 0) { n /= 3; ++threes; }
+  while (n % 5 == 0) { n /= 5; ++fives; }
+  while (twos >= 4) { r.push_back(16); twos -= 4; }
+  if (twos == 3) r.push_back(8);
   if (twos == 2) r.push_back(4);
   if (twos == 1) r.push_back(2);
-  for (int p : {3, 5, 7}) while (n % p == 0) { n /= p; r.push_back(p); }
+  while (threes >= 2) { r.push_back(9); threes -= 2; }
+  if (threes) r.push_back(3);
+  while (fives >= 2) { r.push_back(25); fives -= 2; }
+  if (fives) r.push_back(5);
+  while (n % 7 == 0) { n /= 7; r.push_back(7); }
   if (n != 1) r.clear();
   return r;
 }

@@ -927,7 +927,7 @@ static uint32_t make_sample_tmap(const void* d_samples, uint64_t total_samples, 
 }
 
 int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, const void* d_samples, uint64_t total_samples, int dtype,
-                      const PskTile* d_tiles, uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo) {
+                      const PskTile* d_tiles, uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo, int edge_ctas) {
   int rc;
   MmaTables* T = get_tables(h, d, taps, &rc);
   if (!T || !T->usable) return rc ? rc : FB_EUNSUPPORTED;
@@ -956,7 +956,13 @@ int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, c
   }
   FB_CUDA(h, cudaMemsetAsync(d_redo, 0, 8, h->stream));
   const int smem = Smem<S>::TOTAL;
-  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
+  // One persistent CTA per SM -- minus the SMs left to the float64 edge kernel that runs beside this one (32-thread CTAs, 8 to
+  // an SM).  A CTA of this kernel takes 61 440 of an SM's 65 536 registers, so an edge CTA (4 096) fits beside it only when
+  // nothing else holds a register on that SM; in a process whose NCCL communicator has NVLS enabled that is no longer true
+  // (measured on 2 GPUs: 13.0 ms per step with no SM left free, 9.7 with one, 5.8 with two; 6.0 without NCCL at all).
+  int reserve = edge_ctas > 0 ? std::min(std::max(1, (edge_ctas + 7) / 8), h->sm_count / 8) : 0;
+  if (const char* e = getenv("FB_MMA_GRID_MINUS")) reserve = std::max(0, atoi(e));             // tuning knob
+  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, h->sm_count - reserve));
 #define FB_MMA_LAUNCH(TIN)                                                                                              \
   do {                                                                                                                  \
     FB_CUDA(h, cudaFuncSetAttribute(psk_mma_kernel<TIN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \

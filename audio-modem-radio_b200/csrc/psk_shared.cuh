@@ -13,5 +13,5 @@ struct __align__(16) PskTile {
 bool fb_psk_mma_usable(fb_handle* h, const fb_psk_design& d, const float* taps);
 int fb_psk_mma_tile_syms();
 int fb_psk_mma_launch(fb_handle* h, const fb_psk_design& d, const float* taps, const void* d_samples, uint64_t total_samples, int dtype,
-                      const PskTile* d_tiles, uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo);
+                      const PskTile* d_tiles, uint32_t n_tiles, uint32_t* d_bits, uint32_t* d_redo, int edge_ctas);
 void fb_psk_mma_release(fb_handle* h);

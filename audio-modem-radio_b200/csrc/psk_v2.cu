@@ -862,7 +862,8 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
     // interior tiles on the tensor pipe (psk_mma.cu); the few tiles it hands back (samples outside the fp16 split's range)
     // are then evaluated by the fp32 kernel below, CTAs striding over the redo list
     if (h->profiling) FB_CUDA(h, cudaEventRecord(h->ev_k0, h->stream));
-    int rc = fb_psk_mma_launch(h, d, taps, ma.samples, total_samples, dtype, ma.tiles, n_tiles, ma.bits, (uint32_t*)h->redo.p);
+    int rc = fb_psk_mma_launch(h, d, taps, ma.samples, total_samples, dtype, ma.tiles, n_tiles, ma.bits, (uint32_t*)h->redo.p,
+                               (ea.n_jobs > 0 && !getenv("FB_PSK_NO_EDGE")) ? (int)((ea.n_jobs + 31) / 32) : 0);
     if (rc) return rc;
     if (h->profiling) { FB_CUDA(h, cudaEventRecord(h->ev_k1, h->stream)); h->k_recorded = true; }
     ma.redo = (const uint32_t*)h->redo.p;
@@ -1007,11 +1008,14 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
   // 3 doubles of scratch per sample.  Bounded by half of the free device memory (2^26 samples at most) instead of a fixed
   // 4 M samples, so that a 3-minute recording of such a set returns the reference's bytes as well.
   const uint64_t EMU_MAX = 1ull << 26;
-  uint64_t emu_budget = 0;
-  {
-    size_t fr = 0, tot = 0;
-    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) emu_budget = (uint64_t)fr / 2 / 8; else cudaGetLastError();
-  }
+  uint64_t emu_budget = ~0ull;             // doubles; queried on the first whole-record job only (cudaMemGetInfo is not free)
+  auto emu_budget_doubles = [&]() -> uint64_t {
+    if (emu_budget == ~0ull) {
+      size_t fr = 0, tot = 0;
+      if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) emu_budget = (uint64_t)fr / 2 / 8; else { cudaGetLastError(); emu_budget = 0; }
+    }
+    return emu_budget;
+  };
   for (int r = 0; r < n_rec; ++r) {
     RecPlan& p = plans[r];
     p.off = offsets[r];
@@ -1042,7 +1046,7 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
       }
     }
     if (whole) {
-      if (p.n > EMU_MAX || scratch_doubles + 3 * p.n + 4096 > emu_budget + h->scratch.cap / 8) { p.status = FB_ST_UNSUPPORTED; p.ndsym = 0; continue; }
+      if (p.n > EMU_MAX || scratch_doubles + 3 * p.n + 4096 > emu_budget_doubles() + h->scratch.cap / 8) { p.status = FB_ST_UNSUPPORTED; p.ndsym = 0; continue; }
       make_job(d, r, N, 0, p.nsym - 1, scratch_doubles, jobs);
     }
   }

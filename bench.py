@@ -332,7 +332,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    binding = bind_rank_to_gpu_cpus(local, world) if args.impl != "reference" else None
+    binding = bind_rank_to_gpu_cpus(local, world) if args.impl != "reference" and not os.environ.get("FB_BENCH_NO_BIND") else None
     workload = f"qpsk{BAUD}_c{int(CARRIER)}_{args.recordings}x{args.seconds}s_f32"
     config = {"workload": workload, "scheme": "DQPSK (modem.qpsk_demodulate)", "baud": BAUD, "carrier_hz": CARRIER,
               "fs_hz": FS, "recordings_per_gpu": args.recordings, "seconds_per_recording": args.seconds,
@@ -443,6 +443,7 @@ def main():
         step()                                                               # sampler has a few readings (untimed)
         eng.sync()
     clk = clocks.stop()
+    print(f"[bench] rank {rank} (cuda:{local}): {total_ms / args.steps:.3f} ms per step, interior kernel {np.mean(kernel_ms):.3f} ms", file=sys.stderr, flush=True)
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
