@@ -477,10 +477,11 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
       const uint32_t e8 = (uint32_t)(e0 >> 3);          // (e0 is a multiple of 8 and below 2^35: 32-bit arithmetic)
       const uint32_t c1 = e8 / (S::SEG / 8), c0 = (e8 - c1 * (S::SEG / 8)) * 8;
       const bool inb = sizeof(TIn) == 4 && w0a >= 0 && w0a + (int64_t)SEGS * S::SEG <= (int64_t)pl.n && (e0 >> 35) == 0 && (uint64_t)c1 + SEGS <= a.tm_rows && !(a.dbg & 1);
+      // the stage was last written (converters) and read (ldmatrix) through the generic proxy; (before this thread's own
+      // stores below, so the fence has nothing of ours to wait for)
+      if (inb) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       misc->tile_s[fs] = tc; misc->pl_s[fs] = pl; misc->inb_s[fs] = inb ? 1 : 0;
       if (inb) {
-        // the stage was last written (converters) and read (ldmatrix) through the generic proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t dst = smem_u32(smem + fs * L::STAGE);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
