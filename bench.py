@@ -546,9 +546,22 @@ def main():
             e2e_pcm16 = {"value": None, "error": str(e)[:200]}
 
     # ---- other schemes' dominant kernels on the same device-resident batch (rank 0, informational) -------------------
+    # every rank measures them on its own batch at the same time; rank 0 reports its own figures plus the sum over all GPUs
     schemes = None
-    if rank == 0 and not args.no_schemes:
+    if not args.no_schemes:
+        if dist is not None:
+            dist.barrier()
         schemes = scheme_kernels(eng, torch, batch, n_rec, n_samp, offsets)
+        if dist is not None:
+            names = sorted(k for k, v in schemes.items() if isinstance(v, dict) and "gsamples_per_s" in v)
+            t = torch.tensor([schemes[k]["gsamples_per_s"] for k in names], dtype=torch.float64, device=dev)
+            ok = torch.tensor([float(len(names))], dtype=torch.float64, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == len(names):             # (a scheme that failed on some rank would change the list)
+                dist.all_reduce(t)
+                for k, v in zip(names, t.tolist()):
+                    schemes[k]["gsamples_per_s_all_gpus"] = round(v, 1)
+                    schemes[k]["n_gpus"] = world
 
     if rank != 0:
         if dist is not None:

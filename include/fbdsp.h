@@ -43,7 +43,8 @@ enum {
   FB_ST_OK = 0,
   FB_ST_EMPTY = 1,       /* fewer than 2 symbols: the reference returns b'' (modem.py:95-96, 211)          */
   FB_ST_TOO_SHORT = 2,   /* N <= filtfilt padlen: the reference raises ValueError (scipy filtfilt)       */
-  FB_ST_UNSUPPORTED = 3  /* parameter set only servable by full-window evaluation and the record is too long */
+  FB_ST_UNSUPPORTED = 3  /* parameter set only servable by whole-record float64 evaluation and the record does not fit (more
+                            than 2^26 samples, or 24 bytes of scratch per sample exceed half of the free device memory) */
 };
 
 typedef struct fb_handle fb_handle;
@@ -189,7 +190,8 @@ int fb_parse_frames_batch(fb_handle* h, int n_rec, const uint8_t* raw, const uin
 /* ---- WAV ingest on the device: replaces the host steps of decode_wav_file (decoder.py:381-387) ---------------------------
  * in: n_frames interleaved frames of n_channels samples (FB_S16 = WAV PCM16, scaled by 1/32768 as soundfile does; FB_F32;
  * FB_F64); channel 0 is kept (data[:, 0], decoder.py:382).  out: n_out float64 samples = scipy.signal.resample(channel0,
- * n_out) (FFT method, decoder.py:385-387: n_out = int(round(n_frames * 96000 / sr))); n_out == n_frames just converts.
+ * n_out) (FFT method, decoder.py:385-387: n_out = int(round(n_frames * 96000 / sr)); the transforms are the library's own
+ * float64 FFT, csrc/fft.cu, any length); n_out == n_frames just converts.
  * FB_SAMPLES_ON_DEVICE / FB_OUT_ON_DEVICE say where in / out live; the result can be fed to the *_demod_batch calls as
  * FB_F64 without leaving the device.                                                                                  */
 int fb_ingest_resample(fb_handle* h, const void* in, uint64_t n_frames, int n_channels, int dtype, uint64_t n_out,
