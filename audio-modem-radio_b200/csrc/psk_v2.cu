@@ -885,6 +885,7 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
     else if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2, false);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
     else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0, false);
     else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0, false);
+    else if (ntv == 14 && ma.sps == 20 && ma.P == 1280 && ma.nslow == 1) FB_LAUNCH_MAIN(14, 20, 1280, 1, false);   // 4800 sym/s at 96 kHz (DBPSK-4800)
     else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0, 0, false);
     else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0, 0, false);
     else if (ntv == 18) FB_LAUNCH_MAIN(18, 0, 0, 0, false);
