@@ -205,3 +205,61 @@ extern "C" int fb_debug_fft_c2c(fb_handle* h, const double* host_in_ri, double* 
   FB_CUDA(h, cudaStreamSynchronize(h->stream));
   return FB_OK;
 }
+
+// ---- host execution of the same butterflies (test hook, no GPU needed): tests/test_fft_host.py checks the index math, the
+// radix schedule and the Bluestein chirps against numpy on the CPU ----------------------------------------------------------
+namespace {
+template <int R1, int R2>
+void host_pass(const double2* x, double2* y, int64_t n_total, int64_t cur, int64_t s, int sign) {
+  constexpr int R = R1 * R2;
+  double2 w[R];
+  for (int k = 0; k < R; ++k) fbfft::roots(w, R, k, sign);
+  for (int64_t t = 0; t < n_total / R; ++t) butterfly<R1, R2>(x, y, cur, s, t, sign, w);
+}
+std::vector<double2> host_smooth(std::vector<double2> a, int sign) {
+  const int64_t n = (int64_t)a.size();
+  const std::vector<int> rad = fbfft::smooth_radices(n);
+  std::vector<double2> b(a.size());
+  double2 *x = a.data(), *y = b.data();
+  int64_t cur = n, s = 1;
+  for (int r : rad) {
+    switch (r) {
+#define FB_HOST_PASS(R1, R2) case R1 * R2: host_pass<R1, R2>(x, y, n, cur, s, sign); break
+      FB_HOST_PASS(4, 4); FB_HOST_PASS(4, 2); FB_HOST_PASS(4, 1); FB_HOST_PASS(2, 1); FB_HOST_PASS(3, 3); FB_HOST_PASS(3, 1); FB_HOST_PASS(5, 5); FB_HOST_PASS(5, 1);
+      FB_HOST_PASS(7, 1);
+#undef FB_HOST_PASS
+      default: return {};
+    }
+    cur /= r; s *= r;
+    std::swap(x, y);
+  }
+  return std::vector<double2>(x, x + n);
+}
+}  // namespace
+
+extern "C" int fb_debug_fft_host(const double* in_ri, double* out_ri, int64_t n, int sign) {
+  if (!in_ri || !out_ri || n < 1 || (sign != 1 && sign != -1)) return FB_EINVAL;
+  const double2* in = reinterpret_cast<const double2*>(in_ri);
+  std::vector<double2> res;
+  if (n == 1) res.assign(in, in + 1);
+  else if (!fbfft::smooth_radices(n).empty()) res = host_smooth(std::vector<double2>(in, in + n), sign);
+  else {
+    const int64_t M = fbfft::next_pow2(2 * n - 1);
+    std::vector<double2> a(M), b(M);
+    for (int64_t i = 0; i < M; ++i) {
+      a[i] = i < n ? fbfft::cmul(in[i], fbfft::chirp(i, n, sign)) : make_double2(0.0, 0.0);
+      const int64_t d = i < n ? i : (M - i < n ? M - i : -1);
+      double2 v = make_double2(0.0, 0.0);
+      if (d >= 0) { v = fbfft::chirp(d, n, sign); v.y = -v.y; }
+      b[i] = v;
+    }
+    std::vector<double2> fa = host_smooth(a, -1), fb = host_smooth(b, -1);
+    for (int64_t i = 0; i < M; ++i) fa[i] = fbfft::cmul(fa[i], fb[i]);
+    const std::vector<double2> cv = host_smooth(fa, +1);
+    res.resize(n);
+    for (int64_t k = 0; k < n; ++k) { const double2 v = fbfft::cmul(cv[k], fbfft::chirp(k, n, sign)); res[k] = make_double2(v.x / (double)M, v.y / (double)M); }
+  }
+  if ((int64_t)res.size() != n) return FB_EINVAL;
+  memcpy(out_ri, res.data(), (size_t)n * sizeof(double2));
+  return FB_OK;
+}
