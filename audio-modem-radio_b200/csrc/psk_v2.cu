@@ -202,6 +202,33 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
       const int s = (int)((pl.off + (uint64_t)n_a) & 1);
       if (n_a - s >= 0 && n_a + (int64_t)(ncols + 1) * SPS <= N) {      // whole staged range inside the recording
         const TIn* base = reinterpret_cast<const TIn*>(a.samples) + pl.off + n_a - s;
+        if constexpr (SPS >= 40) {
+          // long columns (1200 sym/s: 80 samples): one column per thread at a time, ten pair loads in flight per step
+          constexpr int CH = 10;
+          static_assert((SPS / 2) % CH == 0, "column length must be a multiple of 20 samples");
+          for (int c = tid; c < ncols + s; c += nthr) {
+            const TIn* src = base + (int64_t)c * SPS;
+            float* dc = X + pm_swz(c);
+#pragma unroll 1
+            for (int i0 = 0; i0 < SPS / 2; i0 += CH) {
+              float2 v[CH];
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = load_pair<TIn>(src + 2 * (i0 + i));
+              if (s) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                  const int e = 2 * (i0 + i);               // loaded elements e, e + 1 -> rows e - 1, e (e - 1 == -1: the previous column's last row)
+                  if (e == 0) { if (c > 0) X[(SPS - 1) * P + pm_swz(c - 1)] = v[i].x; }
+                  else if (c < ncols) dc[(e - 1) * P] = v[i].x;
+                  if (c < ncols) dc[e * P] = v[i].y;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) { dc[2 * (i0 + i) * P] = v[i].x; dc[(2 * (i0 + i) + 1) * P] = v[i].y; }
+              }
+            }
+          }
+        } else {
         constexpr int KC = 4;
         for (int c0 = tid; c0 < ncols + s; c0 += KC * nthr) {
           constexpr int HS = SPS > 1 ? SPS / 2 : 1;
@@ -233,6 +260,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MINB) psk_main_kernel(const __g
               }
             }
           }
+        }
         }
         done = true;
       }
@@ -885,6 +913,7 @@ static int launch_psk(fb_handle* h, PskMainArgs& ma, uint32_t n_tiles, int nthre
     else if (ntv == 16 && ma.sps == 10 && ma.P == 2048 && ma.nslow == 2) FB_LAUNCH_MAIN(16, 10, 2048, 2, false);   // 9600 sym/s at 96 kHz, full-size tiles, one pole pair
     else if (ntv == 16 && ma.sps == 10 && ma.P == 2048) FB_LAUNCH_MAIN(16, 10, 2048, 0, false);
     else if (ntv == 16 && ma.sps == 10) FB_LAUNCH_MAIN(16, 10, 0, 0, false);
+    else if (ntv == 14 && ma.sps == 80 && ma.P == 320 && ma.nslow == 1) FB_LAUNCH_MAIN(14, 80, 320, 1, false);     // 1200 sym/s at 96 kHz (the reference's argument defaults)
     else if (ntv == 14 && ma.sps == 20 && ma.P == 1280 && ma.nslow == 1) FB_LAUNCH_MAIN(14, 20, 1280, 1, false);   // 4800 sym/s at 96 kHz (DBPSK-4800)
     else if (ntv == 14) FB_LAUNCH_MAIN(14, 0, 0, 0, false);
     else if (ntv == 16) FB_LAUNCH_MAIN(16, 0, 0, 0, false);
