@@ -196,16 +196,32 @@ EMULATE_MAX_SAMPLES = 1 << 26            # whole-record float64 evaluation: csrc
 
 
 def has_zero_run(x: np.ndarray, min_run: int) -> bool:
-    """True when x holds at least `min_run` consecutive samples that are exactly zero."""
+    """True when x holds at least `min_run` consecutive samples that are exactly zero.
+
+    A run of >= min_run zeros covers at least one index that is a multiple of min_run, so only every min_run-th sample is
+    inspected (N / min_run reads for a recording without such a run -- every noisy one) and the runs around the zeros found
+    there are measured."""
     n = len(x)
+    min_run = max(1, int(min_run))
     if n < min_run:
         return False
-    nz = np.flatnonzero(x)
-    if len(nz) == 0:
-        return True
-    if nz[0] >= min_run or n - 1 - nz[-1] >= min_run:
-        return True
-    return len(nz) > 1 and int(np.diff(nz).max()) - 1 >= min_run
+    hits = np.flatnonzero(x[::min_run] == 0) * min_run
+    last_end = -1
+    for i in hits:
+        i = int(i)
+        if i <= last_end:                                  # inside a run that was already measured
+            continue
+        lo = max(0, i - min_run + 1)
+        hi = min(n, i + min_run)
+        w = np.flatnonzero(x[lo:hi])                        # non-zero samples of the window around the hit
+        left = w[w < i - lo]
+        right = w[w > i - lo]
+        start = lo + int(left[-1]) + 1 if len(left) else lo
+        end = lo + int(right[0]) if len(right) else hi      # first non-zero after the hit (window end if none)
+        if end - start >= min_run:
+            return True
+        last_end = end
+    return False
 
 
 def emulating_copy(d: PskDesign) -> PskDesign:
