@@ -906,16 +906,15 @@ typedef CUresult (*fb_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static uint32_t make_sample_tmap(const void* d_samples, uint64_t total_samples, CUtensorMap* tm) {
   using S = Sched10;
-  static fb_tmap_encode_fn enc = nullptr;
-  static bool tried = false;
-  memset(tm, 0, sizeof(*tm));
-  if (!tried) {
-    tried = true;
+  // resolved once (function-local static: thread-safe initialisation; handles of several host threads share it)
+  static const fb_tmap_encode_fn enc = []() -> fb_tmap_encode_fn {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (fb_tmap_encode_fn)fn;
-    else cudaGetLastError();
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) return (fb_tmap_encode_fn)fn;
+    cudaGetLastError();
+    return nullptr;
+  }();
+  memset(tm, 0, sizeof(*tm));
   const uint64_t inner = (uint64_t)S::SEG + S::SEGB / 4;          // 164: a box (84 wide) may start anywhere inside its first segment
   if (!enc || getenv("FB_PSK_NO_TMA") || ((uintptr_t)d_samples & 15) || total_samples < inner + (uint64_t)S::SEG * SEGS) return 0;
   const uint64_t rows = (total_samples - inner) / S::SEG + 1;

@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-schemes", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-length raw-byte parity check of recording 0 against the oracle")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configs[N-1]: 2 = the headline (default); 3 / 4 / 5 run sharded through fbdsp.shard (tools/bench_configs.py)")
     ap.add_argument("--scale", type=float, default=1.0, help="configs 3-5: fraction of the stated workload size")
@@ -461,6 +462,22 @@ def main():
     o0 = int(out_offsets[0])                              # spot check of recording 0 against the oracle parser
     want0 = sum(len(fr["data"]) for fr in parse_fbp_stream(out_host[o0:o0 + int(ol[0])].tobytes()))
     assert want0 == int(pbytes_dev[0].item()), "device frame parser disagrees with the oracle"
+    # full-length raw-byte parity of recording 0 of this rank (17.28 M samples at the default size): every byte the reference's
+    # qpsk_demodulate returns -- also before the sync word and after the frame -- and the sync index, against the oracle (untimed)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import modem_v2 as o2
+        t_p = time.perf_counter()
+        st0 = o2.qpsk_stages(batch[:n_samp].cpu().numpy(), BAUD, CARRIER)
+        got0 = out_host[o0:o0 + int(ol[0])].tobytes()
+        parity = {"recording": 0, "samples": int(n_samp), "raw_bytes": len(st0["raw"]), "raw_bytes_equal": got0 == st0["raw"],
+                  "sync_idx_equal": int(sync_idx[0].item()) == int(st0["sync"]), "oracle_s": round(time.perf_counter() - t_p, 2),
+                  "against": "oracle/modem_v2.qpsk_stages (restatement of modem.py:189-266, pinned by tests/golden)"}
+        if not parity["raw_bytes_equal"]:                 # reported, not fatal: the line still carries the measurement
+            a_, b_ = np.frombuffer(got0, np.uint8), np.frombuffer(st0["raw"], np.uint8)
+            m_ = min(len(a_), len(b_))
+            parity["differing_bytes"] = int(np.count_nonzero(a_[:m_] != b_[:m_])) + abs(len(a_) - len(b_))
+            print(f"[bench] WARNING: full-length parity of recording 0 failed: {parity}", file=sys.stderr, flush=True)
     if dist is not None:
         t = torch.tensor([raw_bytes, payload_ok], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
@@ -606,7 +623,7 @@ def main():
             "payload_bytes_valid": payload_all, "payload_bytes_sent_rank0": payload_bytes_in,
             "gsamples_per_s_per_gpu": value / 1e3 / world, "gpu_launches": int(launches), "clocks": clk,
             "e2e": (e2e_pcm16 if (e2e_pcm16 and e2e_pcm16.get("value")) else e2e), "roofline": roofline, "cpu_baseline": cb,
-            "e2e_f32": e2e, "schemes": schemes}
+            "e2e_f32": e2e, "schemes": schemes, "parity_spot_check": parity}
     print(json.dumps(line), file=result_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
