@@ -104,7 +104,7 @@ int c2c_smooth(fb_handle* h, double2* a, double2* b, int64_t n, int sign, const 
     const int g = grid_for(count);
     switch (r) {
 #define FB_FFT_PASS(R1, R2) case R1 * R2: fft_pass_kernel<R1, R2><<<g, FB_THREADS, 0, h->stream>>>(x, y, cur, s, count, sign); break
-      FB_FFT_PASS(4, 4); FB_FFT_PASS(4, 2); FB_FFT_PASS(4, 1); FB_FFT_PASS(2, 1); FB_FFT_PASS(3, 3); FB_FFT_PASS(3, 1); FB_FFT_PASS(5, 5); FB_FFT_PASS(5, 1);
+      FB_FFT_PASS(4, 8); FB_FFT_PASS(3, 9); FB_FFT_PASS(4, 4); FB_FFT_PASS(4, 2); FB_FFT_PASS(4, 1); FB_FFT_PASS(2, 1); FB_FFT_PASS(3, 3); FB_FFT_PASS(3, 1); FB_FFT_PASS(5, 5); FB_FFT_PASS(5, 1);
       FB_FFT_PASS(7, 1);
 #undef FB_FFT_PASS
       default: return FB_EINVAL;
@@ -225,7 +225,7 @@ std::vector<double2> host_smooth(std::vector<double2> a, int sign) {
   for (int r : rad) {
     switch (r) {
 #define FB_HOST_PASS(R1, R2) case R1 * R2: host_pass<R1, R2>(x, y, n, cur, s, sign); break
-      FB_HOST_PASS(4, 4); FB_HOST_PASS(4, 2); FB_HOST_PASS(4, 1); FB_HOST_PASS(2, 1); FB_HOST_PASS(3, 3); FB_HOST_PASS(3, 1); FB_HOST_PASS(5, 5); FB_HOST_PASS(5, 1);
+      FB_HOST_PASS(4, 8); FB_HOST_PASS(3, 9); FB_HOST_PASS(4, 4); FB_HOST_PASS(4, 2); FB_HOST_PASS(4, 1); FB_HOST_PASS(2, 1); FB_HOST_PASS(3, 3); FB_HOST_PASS(3, 1); FB_HOST_PASS(5, 5); FB_HOST_PASS(5, 1);
       FB_HOST_PASS(7, 1);
 #undef FB_HOST_PASS
       default: return {};

@@ -3,7 +3,7 @@
 //   * scipy.signal.resample inside decoder.py:385-387 (WAV files that are not at 96 kHz): forward, crop / pad, inverse.
 // Both are defined by a length-N DFT of the WHOLE record (N is whatever the file holds: 17 280 000 = 2^10 3^3 5^4 for three
 // minutes at 96 kHz), so the transform has to take any N:
-//   * N = 2^a 3^b 5^c 7^d: out-of-place Stockham autosort passes (decimation in frequency), radix 8 / 4 / 2 / 3 / 5 / 7,
+//   * N = 2^a 3^b 5^c 7^d: out-of-place Stockham autosort passes (decimation in frequency), radix 32 / 16 / 8 / 4 / 2 / 27 / 9 / 3 / 25 / 5 / 7,
 //     one pass = one streaming read + one streaming write of the N complex128 points, twiddles by sincospi on exact
 //     integer fractions (no table, no accumulated rotation: relative error ~ log2(N) ulp);
 //   * any other N: Bluestein's chirp-z over a power-of-two length M >= 2N - 1 with the same pass kernels, chirp phases from
@@ -78,23 +78,29 @@ __host__ __device__ __forceinline__ void butterfly(const double2* __restrict__ x
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) a[k1 * R2 + i2] = (k1 * i2) % R == 0 ? v[k1] : cmul(v[k1], w[(k1 * i2) % R]);
   }
+  // pass twiddles exp(sign 2 pi i p k / n), k = k1 + R1 k2: one sincospi per k1 and one for the step exp(sign 2 pi i p R1 / n),
+  // the powers along k2 by multiplication (at most R2 - 1 <= 8 steps: a few ulp; a sincospi per output made the composite
+  // passes compute-bound)
   double2* yo = y + q + s * (R * p);
+  const double2 stepw = R2 > 1 ? unit(p * R1, n, sign) : make_double2(1.0, 0.0);
 #pragma unroll
   for (int k1 = 0; k1 < R1; ++k1) {
     double2 v[R2];
 #pragma unroll
     for (int i2 = 0; i2 < R2; ++i2) v[i2] = a[k1 * R2 + i2];
     dft_small<R2>(v, w, R1, sign);
+    double2 tw = k1 == 0 ? make_double2(1.0, 0.0) : unit(p * k1, n, sign);
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) {
       const int k = k1 + R1 * k2;
-      yo[k * s] = k == 0 ? v[k2] : cmul(v[k2], unit(p * k, n, sign));
+      yo[k * s] = k == 0 ? v[k2] : cmul(v[k2], tw);
+      if (k2 + 1 < R2) tw = cmul(tw, stepw);
     }
   }
 }
 
 // the R-th roots of unity a pass needs (R <= FFT_MAX_RADIX)
-constexpr int FFT_MAX_RADIX = 25;
+constexpr int FFT_MAX_RADIX = 32;
 __host__ __device__ __forceinline__ void roots(double2* w, int R, int k, int sign) { w[k] = unit(k, R, sign); }
 
 // Bluestein chirp w(i) = exp(sign * pi * i * i^2 / n), the phase from i^2 mod 2n in exact integers (i < 2^31)
@@ -105,7 +111,7 @@ __host__ __device__ __forceinline__ double2 chirp(int64_t i, int64_t n, int sign
   return make_double2(c, sign < 0 ? -s : s);
 }
 
-// radices of a {2,3,5,7}-smooth length (composite radices 16 / 9 / 25 first: a pass is one read and one write of all the
+// radices of a {2,3,5,7}-smooth length (composite radices 32 / 16 / 27 / 9 / 25 first: a pass is one read and one write of all the
 // points, so fewer passes; the radix-R butterfly is a direct R x R product); empty when n has another prime factor
 inline std::vector<int> smooth_radices(int64_t n) {
   std::vector<int> r;
@@ -114,12 +120,14 @@ inline std::vector<int> smooth_radices(int64_t n) {
   while (n % 2 == 0) { n /= 2; ++twos; }
   while (n % 3 == 0) { n /= 3; ++threes; }
   while (n % 5 == 0) { n /= 5; ++fives; }
-  while (twos >= 4) { r.push_back(16); twos -= 4; }
+  while (twos >= 5) { r.push_back(32); twos -= 5; }
+  if (twos == 4) r.push_back(16);
   if (twos == 3) r.push_back(8);
   if (twos == 2) r.push_back(4);
   if (twos == 1) r.push_back(2);
-  while (threes >= 2) { r.push_back(9); threes -= 2; }
-  if (threes) r.push_back(3);
+  while (threes >= 3) { r.push_back(27); threes -= 3; }
+  if (threes == 2) r.push_back(9);
+  if (threes == 1) r.push_back(3);
   while (fives >= 2) { r.push_back(25); fives -= 2; }
   if (fives) r.push_back(5);
   while (n % 7 == 0) { n /= 7; r.push_back(7); }
