@@ -499,6 +499,7 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
     };
     if (p == 0) { fetch(0); if (!f_done) fetch(1); }
     uint64_t prev_off = ~0ull;
+    bool prev_ok = false;                              // the previous tile's samples fitted the fp16 split: its carried state is usable
     int prev_d0 = 0;
     for (uint32_t it = 0;; ++it) {
       const int st = it & 1;
@@ -510,8 +511,11 @@ __global__ void __maxnreg__(120) psk_mma_kernel(const __grid_constant__ MmaArgs 
       if (t == ~0u) break;
       if (p == 0 && !f_done) fetch(st);                  // stage st is free: request tile it + 2
       const PskTile pl = misc->pl_u[st];
-      const bool chained = (pl.off == prev_off) && (pl.d0 == prev_d0 + TILE_SYMS);   // forward state carried from the previous tile
+      // forward state carried from the previous tile -- unless that tile went to the redo list: a stretch louder than the
+      // fp16 range turns its products, and with them the carried state, into inf / NaN for the rest of the chunk
+      const bool chained = (pl.off == prev_off) && (pl.d0 == prev_d0 + TILE_SYMS) && prev_ok;
       prev_off = pl.off; prev_d0 = pl.d0;
+      prev_ok = misc->ok[st] != 0;
       // ---- forward slow-pole state at the tile's first group when it cannot be carried: direct sum over the previous wlen
       // samples (exact start-up state of scipy's filtfilt when the record start is within reach; psk_v2.cu has the algebra)
       if (!chained) {                                   // uniform over the post warps

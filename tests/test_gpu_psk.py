@@ -177,3 +177,34 @@ def test_pipelined_host_copy_equals_single_copy(engine, monkeypatch):
     got = engine.psk_demod_batch(recs, d, exact_silence=False)
     assert [(r.raw, r.sync_idx, r.status) for r in got] == [(r.raw, r.sync_idx, r.status) for r in want]
     assert any(len(r.raw) > 100 for r in got)
+
+
+def test_tiles_outside_the_fp16_split_take_the_fp32_kernel(engine, monkeypatch):
+    """psk_mma_kernel hands tiles whose samples do not fit its fp16 hi/lo split (|x| >= 4, or a whole tile below 2^-18) back
+    to the fp32 kernel (redo list).  One recording with a normal, a loud (x 6) and a very quiet (x 1e-6) stretch of several
+    tiles each: the decisions follow the oracle under the same rule as everywhere (mismatches only at margin < 1e-5 or on
+    symbols > 1e-7 below the record's peak), with the tensor-pipe kernel and with the fp32 kernel alone."""
+    import fbdsp
+    rng = np.random.default_rng(4242)
+    parts = []
+    for g in (0.3, 6.0, 1e-6, 0.3):
+        x = sig.qpsk_modulate(bytes(rng.integers(0, 256, 2400, dtype=np.uint8)), baud=9600, carrier=9600.0)
+        parts.append((g * (x + 0.05 * rng.standard_normal(len(x)))).astype(np.float32))
+    x = np.concatenate(parts)
+    assert len(x) > 16 * 18880 and np.abs(x).max() > 4.0
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    st = o2.qpsk_stages(x, 9600, 9600.0)
+    mag = np.abs(st["diff"])
+    margin = o2.qpsk_margin(st["diff"])
+    for no_mma in (False, True):
+        if no_mma:
+            monkeypatch.setenv("FB_PSK_NO_MMA", "1")
+        else:
+            monkeypatch.delenv("FB_PSK_NO_MMA", raising=False)
+        engine.psk_demod_batch([x], d, exact_silence=False)
+        got = engine.last_bits(0)
+        assert len(got) == len(st["bits"])
+        bad = np.unique(np.nonzero(got != st["bits"])[0] // 2)
+        assert len(bad) < 1e-4 * len(mag)
+        for k in bad:
+            assert margin[k] < 1e-5 or mag[k] < 1e-14 * mag.max(), (no_mma, k, margin[k], mag[k] / mag.max())
