@@ -208,3 +208,23 @@ def test_tiles_outside_the_fp16_split_take_the_fp32_kernel(engine, monkeypatch):
         assert len(bad) < 1e-4 * len(mag)
         for k in bad:
             assert margin[k] < 1e-5 or mag[k] < 1e-14 * mag.max(), (no_mma, k, margin[k], mag[k] / mag.max())
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.int16, np.float64])
+def test_every_buffer_alignment_of_a_recording(dt, engine):
+    """Recordings that start at every element offset mod 8 of the batch buffer (the tensor-pipe kernel keeps one set of B
+    fragments per alignment and stages through TMA only float32 tiles whose window start is a multiple of 8 elements), several
+    tiles each, all three storage types: raw bytes and sync index equal the oracle's on the same (int16-exact) samples."""
+    import fbdsp
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    recs = []
+    for i in range(9):
+        _, _, x = sig.kat_signal(sig.qpsk_modulate, 600 + i, 1300, 20, baud=9600, carrier=9600.0)
+        q = np.clip(np.round(x[: 60001 + i] * 32767), -32768, 32767).astype(np.int16)      # lengths 60001 .. 60009: offsets walk mod 8
+        recs.append(q)
+    xs = [q.astype(np.float32) / np.float32(32768.0) for q in recs]
+    arrs = recs if dt == np.int16 else [x.astype(dt) for x in xs]
+    res = engine.psk_demod_batch(arrs, d, exact_silence=False)
+    for x, r in zip(xs, res):
+        want = o2.qpsk_stages(x, 9600, 9600.0)
+        assert r.raw == want["raw"] and r.sync_idx == want["sync"]
