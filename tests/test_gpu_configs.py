@@ -195,3 +195,25 @@ def test_config2_multipart_ofdm8_fec_pipeline(engine):
     files = assemble_stream(frames)
     (f,) = [v for v in files.values() if v["complete"]]
     assert f["data"] == blob and f["size_ok"] and f["crc_ok"]
+
+
+def test_digital_silence_exact_pcm16(engine):
+    """The same for PCM16 storage (a WAV with digital silence before and after the transmission -- what a recorder that gates
+    its input writes) and for DBPSK: every raw byte equals the reference's on the /32768-scaled samples."""
+    import fbdsp
+    _, _, x = sig.kat_signal(sig.qpsk_modulate, 5013, 900, 20, baud=9600, carrier=9600.0)
+    q = np.clip(np.round(x * 20000), -32768, 32767).astype(np.int16)
+    q = np.concatenate([np.zeros(25000, np.int16), q, np.zeros(18000, np.int16)])
+    xf = q.astype(np.float64) / 32768.0
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    st = o2.qpsk_stages(xf, 9600, 9600.0)
+    res = engine.psk_demod_batch([q], d)[0]
+    assert np.array_equal(engine.last_bits(0), st["bits"])
+    assert res.raw == st["raw"] and res.sync_idx == st["sync"]
+    _, _, xb = sig.kat_signal(sig.bpsk_modulate, 5014, 400, 20, baud=9600, carrier=3000.0)
+    qb = np.concatenate([np.zeros(9000, np.int16), np.clip(np.round(xb * 20000), -32768, 32767).astype(np.int16), np.zeros(7000, np.int16)])
+    db = fbdsp.psk_design(9600.0, 3000.0, 96000.0, 1.0, True)
+    sb = o2.bpsk_stages(qb.astype(np.float64) / 32768.0, 9600, 3000.0)
+    rb = engine.psk_demod_batch([qb], db)[0]
+    assert np.array_equal(engine.last_bits(0), sb["bits"])
+    assert rb.raw == sb["raw"] and rb.sync_idx == sb["sync"]
