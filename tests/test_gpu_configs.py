@@ -217,3 +217,18 @@ def test_digital_silence_exact_pcm16(engine):
     rb = engine.psk_demod_batch([qb], db)[0]
     assert np.array_equal(engine.last_bits(0), sb["bits"])
     assert rb.raw == sb["raw"] and rb.sync_idx == sb["sync"]
+
+
+def test_digital_silence_gap_between_two_transmissions(engine):
+    """Two transmissions with a gap of exact zeros between them (no leading / trailing silence): inside the gap the reference's
+    forward pass leaks out of the first and its backward pass out of the second transmission; all bits and bytes equal."""
+    import fbdsp
+    from fbdsp import modem
+    _, _, xa = sig.kat_signal(sig.qpsk_modulate, 5015, 700, 20, baud=9600, carrier=9600.0)
+    _, _, xb = sig.kat_signal(sig.qpsk_modulate, 5016, 500, 25, baud=9600, carrier=9600.0)
+    x = np.concatenate([xa, np.zeros(12345, np.float32), xb])
+    st = o2.qpsk_stages(x, 9600, 9600.0)
+    d = fbdsp.psk_design(9600.0, 9600.0, 96000.0, 1.5, False)
+    res = engine.psk_demod_batch([x], d)[0]
+    assert np.array_equal(engine.last_bits(0), st["bits"])
+    assert res.raw == st["raw"] and modem.qpsk_demodulate(x, 9600, 9600.0) == st["raw"]
