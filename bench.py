@@ -618,6 +618,9 @@ def main():
     cb = None if args.no_cpu else cpu_baseline(30)
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "dtype_note": ("float32 samples; interior symbols: fp16 hi/lo split operands (22 significant bits) on HMMA with fp32 accumulation, "
+                           "slow-pole scan / slicer in fp32; record edges in float64; decisions bit-equal to the float64 reference on every "
+                           "golden case and on recording 0 of this run (parity_spot_check)"),
             "data": "synthetic", "config": dict(config, frame_parse="device (parse_frames_kernel: FBPC scan + header checks + CRC32), inside the timed step"),
             "raw_MB_per_s": raw_all / (ms_per_step * 1e-3) / 1e6, "payload_MB_per_s": payload_all / (ms_per_step * 1e-3) / 1e6,
             "payload_bytes_valid": payload_all, "payload_bytes_sent_rank0": payload_bytes_in,
