@@ -46,3 +46,31 @@ for name, freq in (("mark", mark), ("space", space)):
     for dist in (0, 10, 100, 1000, 10000, 100000, N // 2):
         if dist + 50 < N:
             print(f"{name}: |local FIR - reference| / peak at {dist:7d} samples from the start {err[dist:dist + 50].max():.2e}, from the end {err[N - 1 - dist - 50: N - dist].max():.2e}")
+
+# ---- the exact decomposition (validated here to 3e-13 of the peak, everywhere including the record ends) ---------------------
+#   a_ref = hilbert(filtfilt(x)) = a~ + d' + j H_circ{d'},
+#   a~  = the local complex FIR applied to the zero-extended record, its tails beyond [0, N) wrapped around (periodised),
+#   d'  = filtfilt(x) - Re(a~): non-zero only within ~T samples of the two record ends (1e-13 inside),
+#   H_circ{d'}[n] far from the ends = (2 / N) * sum over the m of opposite parity of d'[m] cot(pi (n - m) / N): one moment of d'
+#   per parity is accurate to 2e-9 of the peak at 20 000 samples from an end, two moments to 5e-12 (checked with /tmp runs).
+print()
+for name, freq in (("mark", mark), ("space", space)):
+    aex, (b, a) = exact(freq)
+    g, L = kernel(b, a)
+    mag = np.abs(g) / np.abs(g).max()
+    idx = np.nonzero(mag > 1e-13)[0]
+    lo, hi = idx[0] - L, idx[-1] - L
+    full = np.convolve(x, g[L + lo: L + hi + 1])             # linear convolution; index 0 <-> output sample `lo`
+    aper = full[-lo: -lo + N].copy()
+    aper[:hi] += full[-lo + N: -lo + N + hi]                  # right tail wraps to the start
+    aper[N + lo:] += full[:-lo]                               # left tail wraps to the end
+    filt = aex.real
+    peak = np.abs(aex).max()
+    delta = filt - aper.real
+    T = 4000
+    d2 = np.zeros(N)
+    d2[:T] = delta[:T]
+    d2[-T:] = delta[-T:]
+    res = np.abs(aper + signal.hilbert(d2) - aex) / peak
+    print(f"{name}: max|d'| / peak more than {T} samples from an end {np.abs(delta[T:N - T]).max() / peak:.1e}; "
+          f"residual of periodised local FIR + circular analytic signal of the edge term {res.max():.1e}")
