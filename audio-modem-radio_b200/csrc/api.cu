@@ -92,7 +92,7 @@ extern "C" void fb_destroy(fb_handle* h) {
   fb_resample_release(h);
   fb_psk_mma_release(h);
   DevBuf* bufs[] = {&h->in, &h->out, &h->out_len, &h->sync_idx, &h->status, &h->bits, &h->plans, &h->tile_first, &h->tiles,
-                    &h->jobs, &h->scratch, &h->taps, &h->slow_w, &h->sync_raw, &h->fec_in, &h->fec_out, &h->fec_meta, &h->misc, &h->redo, &h->mma_trace, &h->fftws};
+                    &h->jobs, &h->scratch, &h->taps, &h->slow_w, &h->sync_raw, &h->fec_in, &h->fec_out, &h->fec_meta, &h->misc, &h->redo, &h->mma_trace, &h->fftws, &h->psk_tabs};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   cudaEventDestroy(h->ev_fork);

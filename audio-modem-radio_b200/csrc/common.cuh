@@ -52,10 +52,14 @@ struct fb_handle {
   std::string err;
   // device workspace (grown on demand, never shrunk)
   DevBuf in, out, out_len, sync_idx, status, bits, plans, tile_first, tiles, jobs, scratch, taps, slow_w, sync_raw;
-  DevBuf fec_in, fec_out, fec_meta, misc, redo, mma_trace, fftws;
+  DevBuf fec_in, fec_out, fec_meta, misc, redo, mma_trace, fftws, psk_tabs;
   std::vector<void*> mma_cache;   // psk_mma.cu: tensor-core tables per design (host + device copies), built once
   // host copy of the last PSK plan (fb_psk_last_bits)
   std::vector<RecPlan> last_plans;
+  // fp32 DPSK kernel: the design-dependent tables of the last call (psk_tabs on the device, the constant-bank part on the host);
+  // a call with the same design and taps re-uses them instead of rebuilding and uploading
+  std::vector<unsigned char> psk_tab_key;
+  std::vector<unsigned char> psk_tab_host;
   int last_bps = 0;
 };
 

@@ -1119,11 +1119,21 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
     //   pwv  [nslow][wlen+1]    p^k                                 tile-boundary state sums
     //   tbl  [nslow][SLOW_TBL]  m^l, m^(2^st), M^w                  scan multipliers, lam = p^sps, m = lam^PM_CH, M = m^32
     ma.wc_off = d.sps * ntp;
+    const int npairs = std::max(1, (d.nslow + 1) / 2), ns_ = std::max(1, d.nslow);
+    const int wpad = (wlen + 1 + 1024 + 3) / 4 * 4;
+    const size_t o_tb = ((size_t)npairs * wpad * 4 * 4 + 255) / 256 * 256, tab_bytes = o_tb + (size_t)ns_ * SLOW_TBL * 2 * 4;
+    // the tables depend on the design and the taps only: built and uploaded once per parameter set, not per call
+    std::vector<unsigned char> key(sizeof(d) + (size_t)d.sps * d.nt * 8 + 8);
+    memcpy(key.data(), &d, sizeof(d));
+    memcpy(key.data() + sizeof(d), taps, (size_t)d.sps * d.nt * 8);
+    memcpy(key.data() + sizeof(d) + (size_t)d.sps * d.nt * 8, &ntp, 4);
+    memcpy(key.data() + sizeof(d) + (size_t)d.sps * d.nt * 8 + 4, &wlen, 4);
+    const bool tab_hit = h->psk_tabs.p && h->psk_tabs.cap >= tab_bytes && key == h->psk_tab_key && h->psk_tab_host.size() == sizeof(ma.tab);
+    if (tab_hit) memcpy(ma.tab, h->psk_tab_host.data(), sizeof(ma.tab));
+    else {
     for (int j = 0; j < d.sps; ++j)
       for (int t = 0; t < d.nt; ++t)
         ma.tab[j * ntp + t] = make_float2(taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2], taps[((size_t)j * d.nt + (d.nt - 1 - t)) * 2 + 1]);
-    const int npairs = std::max(1, (d.nslow + 1) / 2), ns_ = std::max(1, d.nslow);
-    const int wpad = (wlen + 1 + 1024 + 3) / 4 * 4;
     std::vector<float> pwv((size_t)npairs * wpad * 4, 0.f), tbl((size_t)ns_ * SLOW_TBL * 2, 0.f);
     for (int i = 0; i < d.nslow; ++i) {
       const double pr = d.slow_p[2 * i], pi = d.slow_p[2 * i + 1];
@@ -1154,12 +1164,15 @@ extern "C" int fb_psk_demod_batch(fb_handle* h, const fb_psk_design* dp, const f
       for (int st = 0; st < 5; ++st) { cpowd(cr, ci, 1 << st, tr_, ti_); tb[2 * (32 + st)] = (float)tr_; tb[2 * (32 + st) + 1] = (float)ti_; }
       for (int w = 0; w < 9; ++w) { cpowd(mr, mi, w, tr_, ti_); tb[2 * (37 + w)] = (float)tr_; tb[2 * (37 + w) + 1] = (float)ti_; }
     }
-    const size_t o_tb = (pwv.size() * 4 + 255) / 256 * 256, tab_bytes = o_tb + tbl.size() * 4;
-    if ((rc = fb_ensure(h, h->taps, tab_bytes))) return rc;
-    char* tabs = (char*)h->taps.p;
-    FB_CUDA(h, cudaMemcpyAsync(tabs, pwv.data(), pwv.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    FB_CUDA(h, cudaMemcpyAsync(tabs + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    h->psk_tab_key.clear();
+    if ((rc = fb_ensure(h, h->psk_tabs, tab_bytes))) return rc;
+    FB_CUDA(h, cudaMemcpyAsync((char*)h->psk_tabs.p, pwv.data(), pwv.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    FB_CUDA(h, cudaMemcpyAsync((char*)h->psk_tabs.p + o_tb, tbl.data(), tbl.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // the std::vector staging above is pageable: cudaMemcpyAsync has copied it out before returning
+    h->psk_tab_host.assign(reinterpret_cast<const unsigned char*>(ma.tab), reinterpret_cast<const unsigned char*>(ma.tab) + sizeof(ma.tab));
+    h->psk_tab_key = key;
+    }
+    char* tabs = (char*)h->psk_tabs.p;
     if ((rc = fb_ensure(h, h->tiles, (size_t)std::max<uint32_t>(1, n_tiles) * sizeof(PskTile)))) return rc;
     if (use_mma && (rc = fb_ensure(h, h->redo, ((size_t)n_tiles + 4) * 4))) return rc;
     if (n_tiles > 0) {
