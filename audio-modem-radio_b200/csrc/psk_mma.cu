@@ -89,11 +89,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
       ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-  return ok != 0;
-}
 // Hand-off barriers between the roles: hardware named barriers (bar.arrive by the producers, bar.sync by the consumers), so that
 // a waiting warp costs no issue slots and no shared-memory traffic (polling mbarriers took 47 % of the executed instructions).
 // Each barrier is used once per tile and stage, producers + consumers threads; ids 4 .. 9 (0: __syncthreads, 2: post, 3: loaders).
@@ -111,14 +106,10 @@ __device__ __forceinline__ void hmma(float (&d)[4], const uint32_t (&a)[4], cons
 __device__ __forceinline__ void tr_mark(const MmaArgs& a, uint32_t it, int slot, bool who) {
   if (a.trace && who && it < TR_TILES) a.trace[((size_t)blockIdx.x * TR_TILES + it) * 16 + slot] = clock64();
 }
-__device__ __forceinline__ void bar_mma() { asm volatile("bar.sync 1, %0;" ::"n"(MMA_THREADS) : "memory"); }
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ float2 cfmaf(float2 a, float2 b, float2 c) {   // a*b + c
   return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
-}
-__device__ __forceinline__ float2 mapf(float4 m, float2 f, float2 acc) {  // acc + [m.x m.y; m.z m.w] (f.x, f.y)
-  return make_float2(fmaf(m.x, f.x, fmaf(m.y, f.y, acc.x)), fmaf(m.z, f.x, fmaf(m.w, f.y, acc.y)));
 }
 
 // One staging unit = 8 consecutive samples starting at element e (a multiple of 8: 16-byte aligned for every storage type).
