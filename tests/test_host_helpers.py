@@ -30,3 +30,16 @@ def test_emulating_copy_is_independent():
     for f in ("sps", "n0", "bits_per_sym", "pad_bp", "pad_lp", "w_bp", "w_lp"):
         assert getattr(e.c_struct, f) == getattr(d.c_struct, f)
     assert list(e.c_struct.bp_b) == list(d.c_struct.bp_b) and list(e.c_struct.lp_a) == list(d.c_struct.lp_a)
+
+
+def test_has_zero_run_against_brute_force():
+    rng = np.random.default_rng(12345)
+    for _ in range(1500):
+        n, run = int(rng.integers(1, 300)), int(rng.integers(1, 40))
+        x = rng.integers(-1, 2, n).astype(np.float32)
+        if rng.random() < 0.5:
+            a = int(rng.integers(0, n))
+            x[a: min(n, a + int(rng.integers(0, 80)))] = 0
+        z = (x == 0).astype(np.int64)
+        want = n >= run and bool((np.convolve(z, np.ones(run, dtype=np.int64), "valid") >= run).any())
+        assert has_zero_run(x, run) == want, (n, run, x.tolist())
